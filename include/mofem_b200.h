@@ -1,0 +1,140 @@
+/*
+ * mofem_b200.h -- C-ABI of the B200-native stiffness-assembly + PCG path.
+ *
+ * Drop-in boundary for the hot path of junbinhuang/MOFEM (pure Python): these
+ * are the entry points a ctypes binding inside the reference's
+ * linearSolvers/AMORE.py / traditionalElement.py would call (see
+ * INTEGRATION.md for that binding).  Plain pointers and sizes only.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   mofem_set_problem      <- the solvers' inputs: inputData[3..6]
+ *                             (inputFunctions/inputF.py:165,204), polygons /
+ *                             overlappingMesh (computGeometry/planeSweepMeshes.py:354,
+ *                             meshTools/toDC.py:48-72), flattened by mofem_b200/flatten.py
+ *   mofem_symbolic         <- scipy.sparse.coo_matrix(...).tocsr() pattern
+ *                             (AMORE.py:129,404,827; traditionalElement.py:54,204,357)
+ *   mofem_assemble         <- the element / cell loops AMORE.py:42-123, 307-398, 729-821,
+ *                             traditionalElement.py:36-48,188-198,339-351 and the
+ *                             arithmetic of elementLibrary/stiffnessMatrix.py,
+ *                             shapeFunction.py, invShapeFunction.py,
+ *                             otherFunctions/numericalIntegration.py
+ *   mofem_set_system       <- constraint elimination AMORE.py:213-255 (clones :632-674,
+ *                             1055-1097; traditionalElement.py:94-136 ...)
+ *   mofem_solve            <- spsolve(Kglo,fglo) AMORE.py:264,683,1106;
+ *                             traditionalElement.py:146,296,461 (Jacobi-PCG instead of SuperLU)
+ *   mofem_energy           <- 0.5*u^T K u, AMORE.py:278,701,1124
+ *
+ * Error convention: every call returns MOFEM_OK (0) or a negative code;
+ * mofem_last_error() gives the text.  CUDA errors are never swallowed.
+ * The reference's own failures map to codes: MOFEM_E_NEWTON = AssertionError
+ * "Too many iterations!" (invShapeFunction.py:68,102,136), MOFEM_E_ELEMENT =
+ * ValueError "Wrong element numbering!" (AMORE.py:51,74).
+ *
+ * Threading: a context is single-threaded and synchronous (like the reference);
+ * each context owns one CUDA stream on one device.
+ */
+#ifndef MOFEM_B200_H
+#define MOFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOFEM_OK 0
+#define MOFEM_E_CUDA -1      /* CUDA runtime error (text in mofem_last_error) */
+#define MOFEM_E_ARG -2       /* bad argument / call order */
+#define MOFEM_E_NEWTON -3    /* inverse isoparametric map did not converge in 20 updates */
+#define MOFEM_E_ELEMENT -4   /* element node count not supported by the selected solver */
+#define MOFEM_E_NOMEM -5
+#define MOFEM_E_LIMIT -6     /* problem exceeds an index-width limit of this build */
+#define MOFEM_E_NOCONV -7    /* PCG hit maxit before reaching rtol */
+
+typedef struct mofem_ctx mofem_ctx;
+
+/* Flattened problem (SoA).  Pointers may be HOST or DEVICE pointers (detected
+ * with cudaPointerGetAttributes); the context copies what it needs.
+ * Cell order is the reference's emission order: regular elements first, then
+ * overlay cells in `polygons` order. */
+typedef struct {
+    int64_t n_node, n_elem, n_cell, n_tri;
+    int32_t n_mesh, n_mat;
+    int32_t solver;              /* 1 lowerOrderAMORE/FE, 2 quadraticAMORE/FE, 3 quadraticICMAMORE / ICMFE */
+    int32_t _pad;
+    const double *node_xy;       /* [n_node][2], mid-nodes completed by the getCoord rule */
+    const int32_t *elem_nodes;   /* [n_elem][9], -1 padded */
+    const int32_t *elem_nn;      /* [n_elem] in {3,4,6,9} */
+    const int32_t *elem_mat;     /* [n_elem] */
+    const double *mat_D;         /* [n_mat][3][3] */
+    const int32_t *cell_elem;    /* [n_cell][n_mesh] global element id per mesh slot, -1 = none */
+    const int32_t *cell_kind;    /* [n_cell] 0 regular element rule, 1 triangulated overlay cell */
+    const int64_t *cell_tri_ptr; /* [n_cell+1] */
+    const double *tri_xy;        /* [n_tri][3][2] */
+    const double *tri_rho;       /* [n_tri][3][n_mesh] */
+    const double *tri_mid;       /* [n_tri][3][2] mid-edge points of curved triangles, or NULL */
+    const uint8_t *tri_curved;   /* [n_tri] or NULL */
+} mofem_problem_t;
+
+typedef struct {
+    int64_t n_dof;        /* 2*n_node */
+    int64_t nnz;          /* scalar CSR entries (explicit zeros kept) */
+    int64_t n_block;      /* emitted element/cell blocks ("tasks") */
+    int64_t n_coo;        /* COO triplets the reference would emit */
+    int64_t n_pair;       /* 2x2 node-pair sub-blocks integrated */
+    int64_t newton_updates; /* total Newton updates of the last mofem_assemble */
+    int64_t n_eval;       /* (quadrature point, element) evaluations of the last mofem_assemble */
+} mofem_info_t;
+
+typedef struct {
+    int32_t iterations;
+    int32_t converged;
+    double relres_true;   /* ||b-Ax|| / ||b|| recomputed at exit */
+    double relres_rec;    /* recurrence residual at exit */
+    int32_t restarts;     /* times the true residual replaced the recurrence residual */
+    int32_t _pad;
+} mofem_solve_info_t;
+
+/* lifecycle ---------------------------------------------------------- */
+int mofem_create(mofem_ctx **ctx, int device);
+void mofem_destroy(mofem_ctx *ctx);
+const char *mofem_last_error(const mofem_ctx *ctx);
+const char *mofem_version(void);
+/* CUDA stream the context launches on (cudaStream_t as void*), for event timing. */
+void *mofem_stream(mofem_ctx *ctx);
+
+/* assembly ----------------------------------------------------------- */
+int mofem_set_problem(mofem_ctx *ctx, const mofem_problem_t *p);
+int mofem_symbolic(mofem_ctx *ctx);   /* integer phase: CSR pattern + reduction plan */
+int mofem_assemble(mofem_ctx *ctx);   /* integrate all blocks + deterministic reduce into CSR values */
+int mofem_get_info(mofem_ctx *ctx, mofem_info_t *info);
+/* Scalar CSR, identical in pattern to scipy coo->csr.  Output pointers may be host or device; any may be NULL. */
+int mofem_get_csr(mofem_ctx *ctx, int32_t *indptr, int32_t *indices, double *data);
+/* Parity/debug: the COO values (Vglo) in the reference's emission order, host or device pointer. */
+int mofem_get_coo_values(mofem_ctx *ctx, double *V);
+
+/* solve -------------------------------------------------------------- */
+/* rhs: global force vector f (n_dof); fixed: 1 where the DOF is prescribed; fixed_value: prescribed values
+ * (ignored where fixed==0).  Builds b = (f - K*u_fixed) on free DOFs (AMORE.py:227). */
+int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, const double *fixed_value);
+/* Jacobi-preconditioned CG on the free-free block; u (n_dof, host or device) gets fixed values + solution. */
+int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_solve_info_t *info);
+/* 0.5 * u^T K u with the full (unconstrained) K and the u of the last mofem_solve. */
+int mofem_energy(mofem_ctx *ctx, double *energy);
+/* y = K x with the assembled matrix (host or device pointers) -- used by tests and the multi-GPU driver. */
+int mofem_spmv(mofem_ctx *ctx, const double *x, double *y);
+
+/* one-call convenience used for end-to-end timing: host buffers in, host displacement out. */
+int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double *rhs, const uint8_t *fixed,
+                         const double *fixed_value, double rtol, int32_t maxit, double *u,
+                         double *energy, mofem_solve_info_t *info);
+
+/* timing of the last calls, milliseconds measured with CUDA events on the context's stream:
+ * [0] symbolic, [1] integrate kernels, [2] numeric reduce, [3] solve, [4] h2d, [5] d2h.
+ * counts: launches[0..3] = kernel launches in symbolic / integrate / numeric / solve. */
+int mofem_get_timing(mofem_ctx *ctx, double ms[6], int64_t launches[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

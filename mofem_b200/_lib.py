@@ -1,0 +1,110 @@
+"""ctypes binding of libmofem_b200.so (the C-ABI in include/mofem_b200.h).
+
+There is no CPU fallback: if the library is missing or no GPU is present the compute calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmofem_b200.so")
+
+c_d_p = C.POINTER(C.c_double)
+c_i32_p = C.POINTER(C.c_int32)
+c_i64_p = C.POINTER(C.c_int64)
+c_u8_p = C.POINTER(C.c_uint8)
+
+MOFEM_OK = 0
+E_CUDA, E_ARG, E_NEWTON, E_ELEMENT, E_NOMEM, E_LIMIT, E_NOCONV = -1, -2, -3, -4, -5, -6, -7
+
+
+class MofemProblem(C.Structure):
+    _fields_ = [("n_node", C.c_int64), ("n_elem", C.c_int64), ("n_cell", C.c_int64), ("n_tri", C.c_int64),
+                ("n_mesh", C.c_int32), ("n_mat", C.c_int32), ("solver", C.c_int32), ("_pad", C.c_int32),
+                ("node_xy", C.c_void_p), ("elem_nodes", C.c_void_p), ("elem_nn", C.c_void_p), ("elem_mat", C.c_void_p),
+                ("mat_D", C.c_void_p), ("cell_elem", C.c_void_p), ("cell_kind", C.c_void_p), ("cell_tri_ptr", C.c_void_p),
+                ("tri_xy", C.c_void_p), ("tri_rho", C.c_void_p), ("tri_mid", C.c_void_p), ("tri_curved", C.c_void_p)]
+
+
+class MofemInfo(C.Structure):
+    _fields_ = [("n_dof", C.c_int64), ("nnz", C.c_int64), ("n_block", C.c_int64), ("n_coo", C.c_int64),
+                ("n_pair", C.c_int64), ("newton_updates", C.c_int64), ("n_eval", C.c_int64)]
+
+
+class MofemSolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("relres_true", C.c_double),
+                ("relres_rec", C.c_double), ("restarts", C.c_int32), ("_pad", C.c_int32)]
+
+
+# every symbol include/mofem_b200.h declares (tests check the library exports all of them)
+EXPORTS = ("mofem_create", "mofem_destroy", "mofem_last_error", "mofem_version", "mofem_stream", "mofem_set_problem",
+           "mofem_symbolic", "mofem_assemble", "mofem_get_info", "mofem_get_csr", "mofem_get_coo_values",
+           "mofem_set_system", "mofem_solve", "mofem_energy", "mofem_spmv", "mofem_assemble_solve", "mofem_get_timing")
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises RuntimeError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m mofem_b200.build` "
+                           "(mofem_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.mofem_create.argtypes = [C.POINTER(vp), C.c_int]; L.mofem_create.restype = C.c_int
+    L.mofem_destroy.argtypes = [vp]; L.mofem_destroy.restype = None
+    L.mofem_last_error.argtypes = [vp]; L.mofem_last_error.restype = C.c_char_p
+    L.mofem_version.argtypes = []; L.mofem_version.restype = C.c_char_p
+    L.mofem_stream.argtypes = [vp]; L.mofem_stream.restype = vp
+    L.mofem_set_problem.argtypes = [vp, C.POINTER(MofemProblem)]; L.mofem_set_problem.restype = C.c_int
+    L.mofem_symbolic.argtypes = [vp]; L.mofem_symbolic.restype = C.c_int
+    L.mofem_assemble.argtypes = [vp]; L.mofem_assemble.restype = C.c_int
+    L.mofem_get_info.argtypes = [vp, C.POINTER(MofemInfo)]; L.mofem_get_info.restype = C.c_int
+    L.mofem_get_csr.argtypes = [vp, vp, vp, vp]; L.mofem_get_csr.restype = C.c_int
+    L.mofem_get_coo_values.argtypes = [vp, vp]; L.mofem_get_coo_values.restype = C.c_int
+    L.mofem_set_system.argtypes = [vp, vp, vp, vp]; L.mofem_set_system.restype = C.c_int
+    L.mofem_solve.argtypes = [vp, C.c_double, C.c_int32, vp, C.POINTER(MofemSolveInfo)]; L.mofem_solve.restype = C.c_int
+    L.mofem_energy.argtypes = [vp, c_d_p]; L.mofem_energy.restype = C.c_int
+    L.mofem_spmv.argtypes = [vp, vp, vp]; L.mofem_spmv.restype = C.c_int
+    L.mofem_assemble_solve.argtypes = [vp, C.POINTER(MofemProblem), vp, vp, vp, C.c_double, C.c_int32, vp, c_d_p,
+                                       C.POINTER(MofemSolveInfo)]
+    L.mofem_assemble_solve.restype = C.c_int
+    L.mofem_get_timing.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_timing.restype = C.c_int
+    _lib = L
+    return L
+
+
+class MofemError(RuntimeError):
+    pass
+
+
+def raise_for(code, ctx_handle):
+    """Map a C-ABI status to the exception the reference would raise."""
+    if code == MOFEM_OK:
+        return
+    msg = load().mofem_last_error(ctx_handle)
+    msg = msg.decode() if msg else ""
+    if code == E_NEWTON:
+        raise AssertionError(msg or "Too many iterations!")        # invShapeFunction.py:68,102,136
+    if code == E_ELEMENT:
+        raise ValueError(msg or "Wrong element numbering!")        # AMORE.py:51,74
+    if code == E_ARG:
+        raise ValueError(msg)
+    if code == E_NOMEM:
+        raise MemoryError(msg)
+    raise MofemError(f"mofem_b200 error {code}: {msg}")
+
+
+def ptr(a):
+    """Raw address of a numpy array or a torch tensor (host or device), or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))

@@ -1,0 +1,516 @@
+// api.cu -- the C-ABI (include/mofem_b200.h): context, device memory, phase orchestration.
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+
+using namespace mofem;
+
+struct mofem_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // device copies of the problem
+    DevProblem P{};
+    std::vector<void *> problem_allocs;
+    bool have_problem = false, have_symbolic = false, have_matrix = false, have_system = false, have_solution = false;
+    // tasks
+    DevTasks T{};
+    int32_t *cls_tasks = nullptr;
+    int64_t cls_count[N_CLASS]{}, cls_start[N_CLASS]{};
+    int64_t n_pair = 0, n_coo = 0;
+    std::vector<void *> sym_allocs;
+    // csr
+    DevCsr C{};
+    double *data = nullptr, *blk_val = nullptr;
+    unsigned long long *stats = nullptr;  // [4]
+    int *err_flag = nullptr;
+    unsigned long long stats_host[4]{};
+    // solve
+    PcgBuffers W{};
+    uint8_t *fixed = nullptr;
+    double *rhs = nullptr, *fixed_val = nullptr, *u = nullptr;
+    std::vector<void *> sys_allocs;
+    int64_t sys_n = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double ms[6]{};
+    int64_t launches[4]{};
+};
+
+static int ctx_fail(mofem_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CK(call) MOFEM_CUDA_OK(call)
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static int dev_alloc(mofem_ctx *ctx, T **out, int64_t count, std::vector<void *> &pool)
+{
+    *out = nullptr;
+    if (count <= 0) count = 1;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(T) * (size_t)count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx_fail(ctx, MOFEM_E_NOMEM, std::string("cudaMalloc of ") + std::to_string(sizeof(T) * (size_t)count) + " bytes: " + cudaGetErrorString(e));
+    }
+    pool.push_back(p);
+    *out = (T *)p;
+    return MOFEM_OK;
+}
+
+static void free_pool(std::vector<void *> &pool)
+{
+    for (void *p : pool) cudaFree(p);
+    pool.clear();
+}
+
+template <typename T>
+static int upload(mofem_ctx *ctx, const T *src, int64_t count, const T **out, std::vector<void *> &pool)
+{
+    *out = nullptr;
+    if (!src) return MOFEM_OK;
+    T *d = nullptr;
+    int rc = dev_alloc(ctx, &d, count, pool);
+    if (rc) return rc;
+    if (count > 0) CK(cudaMemcpyAsync(d, src, sizeof(T) * (size_t)count, cudaMemcpyDefault, ctx->stream));
+    *out = d;
+    return MOFEM_OK;
+}
+
+static void tic(mofem_ctx *ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+static double toc(mofem_ctx *ctx)
+{
+    float ms = 0;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    return ms;
+}
+
+extern "C" {
+
+const char *mofem_version(void) { return "mofem_b200 0.1.0 (sm_100a)"; }
+
+int mofem_create(mofem_ctx **out, int device)
+{
+    if (!out) return MOFEM_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return MOFEM_E_CUDA; }  // no GPU: fail loudly, no CPU fallback
+    if (device < 0 || device >= ndev) return MOFEM_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MOFEM_E_CUDA;
+    mofem_ctx *ctx = new mofem_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return MOFEM_E_CUDA;
+    }
+    cudaMalloc(&ctx->stats, sizeof(unsigned long long) * 4);
+    cudaMalloc(&ctx->err_flag, sizeof(int));
+    *out = ctx;
+    return MOFEM_OK;
+}
+
+void mofem_destroy(mofem_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_pool(ctx->problem_allocs); free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    cudaFree(ctx->stats); cudaFree(ctx->err_flag);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mofem_last_error(const mofem_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *mofem_stream(mofem_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int mofem_set_problem(mofem_ctx *ctx, const mofem_problem_t *p)
+{
+    if (!ctx || !p) return MOFEM_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (p->n_node < 0 || p->n_elem < 0 || p->n_cell < 0 || p->n_tri < 0 || p->n_mesh < 1 || p->n_mesh > 8 ||
+        p->solver < 1 || p->solver > 3)
+        return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_problem: bad sizes / solver");
+    if (p->n_node >= (1ll << 30)) return ctx_fail(ctx, MOFEM_E_LIMIT, "n_node exceeds 2^30 (int32 DOF indices)");
+    if (!p->node_xy || !p->elem_nodes || !p->elem_nn || !p->elem_mat || !p->mat_D || !p->cell_elem || !p->cell_kind ||
+        !p->cell_tri_ptr || (p->n_tri && (!p->tri_xy || !p->tri_rho)))
+        return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_problem: null array");
+    if ((p->tri_curved != nullptr) != (p->tri_mid != nullptr))
+        return ctx_fail(ctx, MOFEM_E_ARG, "tri_curved and tri_mid must be given together");
+    free_pool(ctx->problem_allocs); free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    ctx->have_problem = ctx->have_symbolic = ctx->have_matrix = ctx->have_system = ctx->have_solution = false;
+    tic(ctx);
+    DevProblem &P = ctx->P;
+    P.n_node = p->n_node; P.n_elem = p->n_elem; P.n_cell = p->n_cell; P.n_tri = p->n_tri;
+    P.n_mesh = p->n_mesh; P.n_mat = p->n_mat; P.solver = p->solver;
+    auto &pool = ctx->problem_allocs;
+    int rc;
+    if ((rc = upload(ctx, p->node_xy, 2 * p->n_node, &P.node_xy, pool))) return rc;
+    if ((rc = upload(ctx, p->elem_nodes, 9 * p->n_elem, &P.elem_nodes, pool))) return rc;
+    if ((rc = upload(ctx, p->elem_nn, p->n_elem, &P.elem_nn, pool))) return rc;
+    if ((rc = upload(ctx, p->elem_mat, p->n_elem, &P.elem_mat, pool))) return rc;
+    if ((rc = upload(ctx, p->mat_D, 9 * (int64_t)p->n_mat, &P.mat_D, pool))) return rc;
+    if ((rc = upload(ctx, p->cell_elem, p->n_cell * p->n_mesh, &P.cell_elem, pool))) return rc;
+    if ((rc = upload(ctx, p->cell_kind, p->n_cell, &P.cell_kind, pool))) return rc;
+    if ((rc = upload(ctx, p->cell_tri_ptr, p->n_cell + 1, &P.cell_tri_ptr, pool))) return rc;
+    if ((rc = upload(ctx, p->tri_xy, 6 * p->n_tri, &P.tri_xy, pool))) return rc;
+    if ((rc = upload(ctx, p->tri_rho, 3 * p->n_tri * p->n_mesh, &P.tri_rho, pool))) return rc;
+    if ((rc = upload(ctx, p->tri_mid, 6 * p->n_tri, &P.tri_mid, pool))) return rc;
+    if ((rc = upload(ctx, p->tri_curved, p->n_tri, &P.tri_curved, pool))) return rc;
+    ctx->ms[4] = toc(ctx);
+    CK(cudaGetLastError());
+    ctx->have_problem = true;
+    return MOFEM_OK;
+}
+
+int mofem_symbolic(mofem_ctx *ctx)
+{
+    if (!ctx || !ctx->have_problem) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_symbolic: call mofem_set_problem first");
+    CK(cudaSetDevice(ctx->device));
+    free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    ctx->have_symbolic = ctx->have_matrix = ctx->have_system = ctx->have_solution = false;
+    cudaStream_t s = ctx->stream;
+    const DevProblem &P = ctx->P;
+    auto &pool = ctx->sym_allocs;
+    int64_t &L = ctx->launches[0];
+    L = 0;
+    tic(ctx);
+    int rc;
+    // --- tasks -------------------------------------------------------------------------
+    int32_t *ntask, *npair, *ncoo;
+    int64_t *task_off, *pair_off, *coo_off;
+    std::vector<void *> tmp;
+    auto cleanup = [&]() { free_pool(tmp); };
+    if ((rc = dev_alloc(ctx, &ntask, P.n_cell, tmp)) || (rc = dev_alloc(ctx, &npair, P.n_cell, tmp)) ||
+        (rc = dev_alloc(ctx, &ncoo, P.n_cell, tmp)) || (rc = dev_alloc(ctx, &task_off, P.n_cell + 1, tmp)) ||
+        (rc = dev_alloc(ctx, &pair_off, P.n_cell + 1, tmp)) || (rc = dev_alloc(ctx, &coo_off, P.n_cell + 1, tmp))) {
+        cleanup(); return rc;
+    }
+#define CKT(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return ctx_fail(ctx, MOFEM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CKT(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
+    CKT(launch_cell_counts(P, ntask, npair, ncoo, ctx->err_flag, s)); L++;
+    CKT(exclusive_scan_i32_to_i64(ntask, task_off, P.n_cell, task_off + P.n_cell, s, &L));
+    CKT(exclusive_scan_i32_to_i64(npair, pair_off, P.n_cell, pair_off + P.n_cell, s, &L));
+    CKT(exclusive_scan_i32_to_i64(ncoo, coo_off, P.n_cell, coo_off + P.n_cell, s, &L));
+    int64_t tot[3]; int eflag = 0;
+    CKT(cudaMemcpyAsync(&tot[0], task_off + P.n_cell, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKT(cudaMemcpyAsync(&tot[1], pair_off + P.n_cell, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKT(cudaMemcpyAsync(&tot[2], coo_off + P.n_cell, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKT(cudaStreamSynchronize(s));
+    if (eflag == MOFEM_E_ELEMENT) { cleanup(); return ctx_fail(ctx, MOFEM_E_ELEMENT, "Wrong element numbering!"); }
+    DevTasks &T = ctx->T;
+    T.n_task = tot[0]; ctx->n_pair = tot[1]; ctx->n_coo = tot[2];
+    if (ctx->n_pair >= (1ll << 31) || T.n_task >= (1ll << 31)) {
+        cleanup();
+        return ctx_fail(ctx, MOFEM_E_LIMIT, "more than 2^31 node pairs on one device: shard the cells over more GPUs");
+    }
+    if ((rc = dev_alloc(ctx, &T.cell, T.n_task, pool)) || (rc = dev_alloc(ctx, &T.e1, T.n_task, pool)) ||
+        (rc = dev_alloc(ctx, &T.e2, T.n_task, pool)) || (rc = dev_alloc(ctx, &T.slots, T.n_task, pool)) ||
+        (rc = dev_alloc(ctx, &T.cls, T.n_task, pool)) || (rc = dev_alloc(ctx, &T.pair_off, T.n_task, pool)) ||
+        (rc = dev_alloc(ctx, &ctx->cls_tasks, T.n_task, pool))) { cleanup(); return rc; }
+    CKT(launch_fill_tasks(P, task_off, pair_off, T, s)); L++;
+    // class buckets
+    int64_t *cls_count_d, *cls_start_d;
+    if ((rc = dev_alloc(ctx, &cls_count_d, N_CLASS, tmp)) || (rc = dev_alloc(ctx, &cls_start_d, N_CLASS, tmp))) { cleanup(); return rc; }
+    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_CLASS, s));
+    CKT(launch_bucket_tasks(T, cls_count_d, nullptr, nullptr, 0, s)); L++;
+    CKT(cudaMemcpyAsync(ctx->cls_count, cls_count_d, sizeof(int64_t) * N_CLASS, cudaMemcpyDeviceToHost, s));
+    CKT(cudaStreamSynchronize(s));
+    int64_t acc = 0;
+    for (int k = 0; k < N_CLASS; k++) { ctx->cls_start[k] = acc; acc += ctx->cls_count[k]; }
+    CKT(cudaMemcpyAsync(cls_start_d, ctx->cls_start, sizeof(int64_t) * N_CLASS, cudaMemcpyHostToDevice, s));
+    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_CLASS, s));
+    CKT(launch_bucket_tasks(T, cls_count_d, cls_start_d, ctx->cls_tasks, 1, s)); L++;
+    // --- CSR symbolic ---------------------------------------------------------------------
+    DevCsr &C = ctx->C;
+    C.n_node = P.n_node;
+    int32_t *row_cnt, *row_uniq;
+    if ((rc = dev_alloc(ctx, &row_cnt, P.n_node, tmp)) || (rc = dev_alloc(ctx, &row_uniq, P.n_node, tmp)) ||
+        (rc = dev_alloc(ctx, &C.row_start, P.n_node + 1, pool)) || (rc = dev_alloc(ctx, &C.node_ptr, P.n_node + 1, pool))) {
+        cleanup(); return rc;
+    }
+    CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
+    CKT(csr_count_rows(P, T, row_cnt, s)); L++;
+    CKT(exclusive_scan_i32_to_i64(row_cnt, C.row_start, P.n_node, C.row_start + P.n_node, s, &L));
+    CKT(cudaMemcpyAsync(&C.n_entry, C.row_start + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKT(cudaStreamSynchronize(s));
+    uint64_t *entries;
+    if ((rc = dev_alloc(ctx, &entries, C.n_entry, tmp))) { cleanup(); return rc; }
+    CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
+    CKT(csr_fill_rows(P, T, C.row_start, row_cnt, entries, s)); L++;
+    CKT(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
+    CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, s)); L++;
+    CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKT(cudaStreamSynchronize(s));
+    if (eflag == MOFEM_E_LIMIT) {  // some node row has > 1024 contributions: redo with a global scratch area
+        uint64_t *scratch;
+        if ((rc = dev_alloc(ctx, &scratch, 2 * C.n_entry, tmp))) { cleanup(); return rc; }
+        CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, scratch, ctx->err_flag, s)); L++;
+    }
+    CKT(exclusive_scan_i32_to_i64(row_uniq, C.node_ptr, P.n_node, C.node_ptr + P.n_node, s, &L));
+    CKT(cudaMemcpyAsync(&C.n_upair, C.node_ptr + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKT(cudaStreamSynchronize(s));
+    if ((rc = dev_alloc(ctx, &C.node_idx, C.n_upair, pool)) || (rc = dev_alloc(ctx, &C.pair_row, C.n_upair, pool)) ||
+        (rc = dev_alloc(ctx, &C.contrib_ptr, C.n_upair + 1, pool)) || (rc = dev_alloc(ctx, &C.contrib_src, C.n_entry, pool)) ||
+        (rc = dev_alloc(ctx, &ctx->data, 4 * C.n_upair, pool)) || (rc = dev_alloc(ctx, &ctx->blk_val, 4 * ctx->n_pair, pool))) {
+        cleanup(); return rc;
+    }
+    CKT(csr_emit(P.n_node, C.row_start, entries, C.node_ptr, C.node_idx, C.pair_row, C.contrib_ptr, C.contrib_src, s)); L++;
+    CKT(cudaMemcpyAsync(C.contrib_ptr + C.n_upair, &C.n_entry, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ctx->ms[0] = toc(ctx);
+    CKT(cudaGetLastError());
+    cleanup();
+#undef CKT
+    ctx->have_symbolic = true;
+    return MOFEM_OK;
+}
+
+int mofem_assemble(mofem_ctx *ctx)
+{
+    if (!ctx || !ctx->have_symbolic) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_assemble: call mofem_symbolic first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    ctx->launches[1] = ctx->launches[2] = 0;
+    CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * 4, s));
+    tic(ctx);
+    for (int k = 0; k < N_CLASS; k++) {
+        if (!ctx->cls_count[k]) continue;
+        CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k], ctx->cls_count[k], ctx->blk_val,
+                                  ctx->stats, s));
+        ctx->launches[1]++;
+    }
+    ctx->ms[1] = toc(ctx);
+    tic(ctx);
+    CK(csr_numeric(ctx->C, ctx->blk_val, ctx->data, s));
+    ctx->launches[2]++;
+    ctx->ms[2] = toc(ctx);
+    CK(cudaMemcpyAsync(ctx->stats_host, ctx->stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (ctx->stats_host[2]) return ctx_fail(ctx, MOFEM_E_NEWTON, "Too many iterations!");
+    ctx->have_matrix = true;
+    ctx->have_system = ctx->have_solution = false;
+    return MOFEM_OK;
+}
+
+int mofem_get_info(mofem_ctx *ctx, mofem_info_t *info)
+{
+    if (!ctx || !info || !ctx->have_symbolic) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_info: no symbolic phase yet");
+    info->n_dof = 2 * ctx->P.n_node;
+    info->nnz = 4 * ctx->C.n_upair;
+    info->n_block = ctx->T.n_task;
+    info->n_coo = ctx->n_coo;
+    info->n_pair = ctx->n_pair;
+    info->newton_updates = (int64_t)ctx->stats_host[0];
+    info->n_eval = (int64_t)ctx->stats_host[1];
+    return MOFEM_OK;
+}
+
+int mofem_get_csr(mofem_ctx *ctx, int32_t *indptr, int32_t *indices, double *data)
+{
+    if (!ctx || !ctx->have_symbolic) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_csr: call mofem_symbolic first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t nnz = 4 * ctx->C.n_upair, nrow = 2 * ctx->P.n_node;
+    if (nnz >= (1ll << 31)) return ctx_fail(ctx, MOFEM_E_LIMIT, "nnz >= 2^31: int32 CSR export not possible");
+    std::vector<void *> tmp;
+    int rc = MOFEM_OK;
+    int32_t *ip = nullptr, *ix = nullptr;
+    if (indptr) { if (is_device_ptr(indptr)) ip = indptr; else if ((rc = dev_alloc(ctx, &ip, nrow + 1, tmp))) return rc; }
+    if (indices) { if (is_device_ptr(indices)) ix = indices; else if ((rc = dev_alloc(ctx, &ix, nnz, tmp))) { free_pool(tmp); return rc; } }
+    cudaError_t e = csr_export_pattern(ctx->C, ip, ix, s);
+    if (e == cudaSuccess && indptr && ip != indptr) e = cudaMemcpyAsync(indptr, ip, sizeof(int32_t) * (nrow + 1), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && indices && ix != indices) e = cudaMemcpyAsync(indices, ix, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && data) {
+        if (!ctx->have_matrix) { free_pool(tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_csr: values requested before mofem_assemble"); }
+        e = cudaMemcpyAsync(data, ctx->data, sizeof(double) * nnz, cudaMemcpyDefault, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    free_pool(tmp);
+    if (e != cudaSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("mofem_get_csr: ") + cudaGetErrorString(e));
+    return MOFEM_OK;
+}
+
+int mofem_get_coo_values(mofem_ctx *ctx, double *V)
+{
+    if (!ctx || !ctx->have_matrix || !V) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_coo_values: call mofem_assemble first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t nt = ctx->T.n_task;
+    // pure re-layout (no arithmetic) of blk_val into the reference's emission order, done on the host
+    std::vector<double> blk((size_t)(4 * ctx->n_pair));
+    std::vector<int32_t> e1(nt), e2(nt), nn((size_t)ctx->P.n_elem);
+    std::vector<int64_t> po(nt);
+    CK(cudaMemcpyAsync(blk.data(), ctx->blk_val, sizeof(double) * blk.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e1.data(), ctx->T.e1, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e2.data(), ctx->T.e2, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(po.data(), ctx->T.pair_off, sizeof(int64_t) * nt, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nn.data(), ctx->P.elem_nn, sizeof(int32_t) * nn.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<double> host;
+    double *out = V;
+    const bool dev_out = is_device_ptr(V);
+    if (dev_out) { host.resize((size_t)ctx->n_coo); out = host.data(); }
+    int64_t off = 0;
+    for (int64_t k = 0; k < nt; k++) {
+        const int n1 = nn[e1[k]], n2 = nn[e2[k]];
+        const double *b = blk.data() + 4 * po[k];
+        for (int a = 0; a < n1; a++)
+            for (int c = 0; c < n2; c++)
+                for (int p = 0; p < 2; p++)
+                    for (int q = 0; q < 2; q++)
+                        out[off + (int64_t)(2 * a + p) * (2 * n2) + 2 * c + q] = b[4 * (a * n2 + c) + 2 * p + q];
+        off += 4ll * n1 * n2;
+        if (e1[k] != e2[k]) {
+            for (int a = 0; a < n1; a++)
+                for (int c = 0; c < n2; c++)
+                    for (int p = 0; p < 2; p++)
+                        for (int q = 0; q < 2; q++)
+                            out[off + (int64_t)(2 * c + q) * (2 * n1) + 2 * a + p] = b[4 * (a * n2 + c) + 2 * p + q];
+            off += 4ll * n1 * n2;
+        }
+    }
+    if (dev_out) { CK(cudaMemcpyAsync(V, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s)); }
+    return MOFEM_OK;
+}
+
+static DevSystem system_of(mofem_ctx *ctx)
+{
+    DevSystem A;
+    A.n = 2 * ctx->P.n_node; A.node_ptr = ctx->C.node_ptr; A.node_idx = ctx->C.node_idx; A.data = ctx->data;
+    return A;
+}
+
+int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, const double *fixed_value)
+{
+    if (!ctx || !ctx->have_matrix) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_system: call mofem_assemble first");
+    if (!rhs || !fixed || !fixed_value) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_system: null array");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t n = 2 * ctx->P.n_node;
+    int rc;
+    if (ctx->sys_n != n || ctx->sys_allocs.empty()) {
+        free_pool(ctx->sys_allocs);
+        auto &pool = ctx->sys_allocs;
+        PcgBuffers &W = ctx->W;
+        if ((rc = dev_alloc(ctx, &W.x, n, pool)) || (rc = dev_alloc(ctx, &W.r, n, pool)) || (rc = dev_alloc(ctx, &W.p, n, pool)) ||
+            (rc = dev_alloc(ctx, &W.q, n, pool)) || (rc = dev_alloc(ctx, &W.dinv, n, pool)) || (rc = dev_alloc(ctx, &W.b, n, pool)) ||
+            (rc = dev_alloc(ctx, &W.ufix, n, pool)) || (rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
+            (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
+            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+            (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
+            (rc = dev_alloc(ctx, &ctx->u, n, pool)))
+            return rc;
+        W.rr_hist = nullptr;
+        ctx->sys_n = n;
+    }
+    tic(ctx);
+    CK(cudaMemcpyAsync(ctx->rhs, rhs, sizeof(double) * n, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(ctx->fixed, fixed, sizeof(uint8_t) * n, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(ctx->fixed_val, fixed_value, sizeof(double) * n, cudaMemcpyDefault, s));
+    ctx->ms[4] += toc(ctx);
+    ctx->launches[3] = 0;
+    CK(pcg_setup(system_of(ctx), ctx->rhs, ctx->fixed, ctx->fixed_val, ctx->W, s, &ctx->launches[3]));
+    CK(cudaStreamSynchronize(s));
+    ctx->have_system = true;
+    ctx->have_solution = false;
+    return MOFEM_OK;
+}
+
+int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_solve_info_t *info)
+{
+    if (!ctx || !ctx->have_system) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_solve: call mofem_set_system first");
+    if (!(rtol > 0) || maxit < 1) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_solve: bad rtol / maxit");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t n = 2 * ctx->P.n_node;
+    mofem_solve_info_t local;
+    if (!info) info = &local;
+    tic(ctx);
+    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, rtol, maxit, 50, info, s, &ctx->launches[3]));
+    CK(pcg_finish(n, ctx->W, ctx->u, s));
+    ctx->launches[3]++;
+    ctx->ms[3] = toc(ctx);
+    ctx->have_solution = true;
+    if (u) {
+        tic(ctx);
+        CK(cudaMemcpyAsync(u, ctx->u, sizeof(double) * n, cudaMemcpyDefault, s));
+        ctx->ms[5] = toc(ctx);
+    }
+    CK(cudaStreamSynchronize(s));
+    if (!info->converged) return ctx_fail(ctx, MOFEM_E_NOCONV, "PCG did not reach rtol within maxit");
+    return MOFEM_OK;
+}
+
+int mofem_energy(mofem_ctx *ctx, double *energy)
+{
+    if (!ctx || !ctx->have_solution || !energy) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_energy: call mofem_solve first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CK(energy_of(system_of(ctx), ctx->u, ctx->W.q, ctx->W.part_c, ctx->W.sc + 5, s));
+    double e = 0;
+    CK(cudaMemcpyAsync(&e, ctx->W.sc + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *energy = 0.5 * e;
+    return MOFEM_OK;
+}
+
+int mofem_spmv(mofem_ctx *ctx, const double *x, double *y)
+{
+    if (!ctx || !ctx->have_matrix || !x || !y) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_spmv: call mofem_assemble first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t n = 2 * ctx->P.n_node;
+    std::vector<void *> tmp;
+    const double *xd = x; double *yd = y;
+    int rc;
+    if (!is_device_ptr(x)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) return rc; CK(cudaMemcpyAsync(t, x, sizeof(double) * n, cudaMemcpyHostToDevice, s)); xd = t; }
+    if (!is_device_ptr(y)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) { free_pool(tmp); return rc; } yd = t; }
+    cudaError_t e = spmv(system_of(ctx), xd, yd, nullptr, s);
+    if (e == cudaSuccess && yd != y) e = cudaMemcpyAsync(y, yd, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    free_pool(tmp);
+    if (e != cudaSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("mofem_spmv: ") + cudaGetErrorString(e));
+    return MOFEM_OK;
+}
+
+int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double *rhs, const uint8_t *fixed,
+                         const double *fixed_value, double rtol, int32_t maxit, double *u, double *energy,
+                         mofem_solve_info_t *info)
+{
+    int rc;
+    if ((rc = mofem_set_problem(ctx, p))) return rc;
+    if ((rc = mofem_symbolic(ctx))) return rc;
+    if ((rc = mofem_assemble(ctx))) return rc;
+    if ((rc = mofem_set_system(ctx, rhs, fixed, fixed_value))) return rc;
+    if ((rc = mofem_solve(ctx, rtol, maxit, u, info))) return rc;
+    if (energy && (rc = mofem_energy(ctx, energy))) return rc;
+    return MOFEM_OK;
+}
+
+int mofem_get_timing(mofem_ctx *ctx, double ms[6], int64_t launches[4])
+{
+    if (!ctx) return MOFEM_E_ARG;
+    if (ms) for (int i = 0; i < 6; i++) ms[i] = ctx->ms[i];
+    if (launches) for (int i = 0; i < 4; i++) launches[i] = ctx->launches[i];
+    return MOFEM_OK;
+}
+
+}  // extern "C"

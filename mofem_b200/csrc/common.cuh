@@ -1,0 +1,116 @@
+// common.cuh -- shared declarations of the mofem_b200 CUDA library (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mofem_b200.h"
+
+namespace mofem {
+
+// cell kinds / task classes -------------------------------------------------------------
+enum { CELL_REGULAR = 0, CELL_OVERLAY = 1 };
+
+// class id of a task (one emitted block):
+//   0..4   regular element rules: tri3, quad4 (quadFE), quad4 (ICMFE), tri6, quad9
+//   8 + 2*(4*i1+i2) + curved   AMORE blocks, i = index of n in {3,4,6,9}
+constexpr int N_CLASS = 8 + 32;
+__host__ __device__ inline int type_index(int nn) { return nn == 3 ? 0 : nn == 4 ? 1 : nn == 6 ? 2 : 3; }
+
+// device view of the flattened problem
+struct DevProblem {
+    int64_t n_node, n_elem, n_cell, n_tri;
+    int32_t n_mesh, n_mat, solver;
+    const double *node_xy;
+    const int32_t *elem_nodes, *elem_nn, *elem_mat;
+    const double *mat_D;
+    const int32_t *cell_elem, *cell_kind;
+    const int64_t *cell_tri_ptr;
+    const double *tri_xy, *tri_rho, *tri_mid;
+    const uint8_t *tri_curved;
+};
+
+// one task = one emitted block (regular element matrix, AMORE diagonal or off-diagonal block)
+struct DevTasks {
+    int64_t n_task;
+    int32_t *cell;      // [n_task]
+    int32_t *e1, *e2;   // [n_task] global element ids (e2 == e1 for diagonal / regular)
+    int32_t *slots;     // [n_task] mesh slot j | (l << 8)
+    int32_t *cls;       // [n_task] class id
+    int64_t *pair_off;  // [n_task] offset of the block in blk_val, in node pairs (x4 doubles)
+};
+
+#define MOFEM_CUDA_OK(call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            return ctx_fail(ctx, MOFEM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                        \
+    } while (0)
+
+// scan.cu
+cudaError_t exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t s,
+                               int64_t *launches);
+cudaError_t exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t s,
+                                      int64_t *launches);
+
+// integrate.cu
+cudaError_t launch_cell_counts(const DevProblem &p, int32_t *ntask, int32_t *npair, int32_t *ncoo, int *err_flag,
+                               cudaStream_t s);
+cudaError_t launch_fill_tasks(const DevProblem &p, const int64_t *task_off, const int64_t *pair_off,
+                              const DevTasks &t, cudaStream_t s);
+cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS] dev, zeroed*/,
+                                const int64_t *cls_start /*[N_CLASS] dev or null*/, int32_t *cls_tasks,
+                                int phase, cudaStream_t s);
+// integrates all tasks of one class; stats[0] += newton updates, stats[1] += evaluations, stats[2] = error flag
+cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *task_list,
+                                   int64_t n_list, double *blk_val, unsigned long long *stats, cudaStream_t s);
+
+// csr.cu
+struct DevCsr {
+    int64_t n_node;    // node rows
+    int64_t n_entry;   // Q: contributions (node pairs incl. transposed copies)
+    int64_t n_upair;   // U: unique node pairs
+    int64_t *row_start;   // [n_node+1] start of each node row in the entry array
+    int64_t *node_ptr;    // [n_node+1] unique pairs per node row (prefix)
+    int32_t *node_idx;    // [U] column node of each unique pair
+    int32_t *pair_row;    // [U] row node of each unique pair
+    int64_t *contrib_ptr; // [U+1] range of contributions of each unique pair
+    uint32_t *contrib_src;// [Q] (pair index in blk_val << 1) | transposed
+};
+cudaError_t csr_count_rows(const DevProblem &p, const DevTasks &t, int32_t *row_cnt, cudaStream_t s);
+cudaError_t csr_fill_rows(const DevProblem &p, const DevTasks &t, const int64_t *row_start, int32_t *row_cursor,
+                          uint64_t *entries, cudaStream_t s);
+cudaError_t csr_sort_rows(int64_t n_node, const int64_t *row_start, uint64_t *entries, int32_t *row_uniq,
+                          uint64_t *scratch, int *err_flag, cudaStream_t s);
+cudaError_t csr_emit(int64_t n_node, const int64_t *row_start, const uint64_t *entries, const int64_t *node_ptr,
+                     int32_t *node_idx, int32_t *pair_row, int64_t *contrib_ptr, uint32_t *contrib_src, cudaStream_t s);
+cudaError_t csr_numeric(const DevCsr &c, const double *blk_val, double *data, cudaStream_t s);
+cudaError_t csr_export_pattern(const DevCsr &c, int32_t *indptr, int32_t *indices, cudaStream_t s);
+
+// pcg.cu
+struct DevSystem {
+    int64_t n;            // scalar unknowns (2 * n_node)
+    const int64_t *node_ptr;
+    const int32_t *node_idx;
+    const double *data;   // scalar CSR values
+};
+cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
+
+constexpr int PCG_MAX_PART = 2048;
+struct PcgBuffers {
+    double *x, *r, *p, *q, *dinv, *b, *ufix;  // n each
+    double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
+    double *sc;                                // 8 scalars
+    double *rr_hist;                           // unused (reserved)
+};
+cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
+                      PcgBuffers &w, cudaStream_t s, int64_t *launches);
+cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, double rtol, int maxit, int chunk,
+                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches);
+cudaError_t pcg_finish(int64_t n, PcgBuffers &w, double *u_dev, cudaStream_t s);
+cudaError_t energy_of(const DevSystem &A, const double *u, double *q_tmp, double *part, double *out_dev, cudaStream_t s);
+
+}  // namespace mofem

@@ -1,0 +1,355 @@
+// pcg.cu -- Jacobi-preconditioned CG on the assembled matrix (replaces scipy spsolve,
+// AMORE.py:264,683,1106; traditionalElement.py:146,296,461).
+//
+// The Dirichlet elimination of the reference (delete fixed rows/columns, AMORE.py:213-255) is applied as a mask:
+// search directions are zero on fixed DOFs and the SpMV zeroes fixed rows, so the iteration is exactly CG on the
+// reduced free-free system without building a second matrix.
+//
+// SpMV reads the scalar CSR values through the node-level pattern (one column index per 2x2 sub-block:
+// 9 bytes per stored scalar instead of 12).  Dot products are two-stage with a fixed reduction order
+// (bit-reproducible); alpha/beta live on the device, the host only polls the residual every few iterations.
+#include "common.cuh"
+
+namespace mofem {
+
+constexpr int VEC_BLOCK = 256;
+constexpr int SPMV_LANES = 8;   // lanes cooperating on one node row
+static_assert(148 * 8 <= PCG_MAX_PART, "partials buffer too small");
+
+// block-wide sum, result valid in every thread; fixed order
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; i++) s += sm[i];
+    return s;
+}
+
+// sum of n partials, every thread of the block gets the same value (fixed order)
+__device__ __forceinline__ double reduce_partials(const double *__restrict__ part, int n, double *sm)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+    return block_sum(v, sm);
+}
+
+// y = K x on node rows [row0,row1); fixed rows -> 0.  Optionally accumulates dot(x,y) partial per block.
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
+       const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
+       const uint8_t *__restrict__ fixed, double *__restrict__ part_dot)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    const int sub = threadIdx.x % SPMV_LANES;
+    const int64_t rows_per_block = VEC_BLOCK / SPMV_LANES;
+    double dot = 0.0;
+    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
+        const int64_t a = row0 + threadIdx.x / SPMV_LANES;
+        double y0 = 0.0, y1 = 0.0;
+        if (a < n_node) {
+            const int64_t r0 = node_ptr[a], deg = node_ptr[a + 1] - r0;
+            const double2 *d0 = reinterpret_cast<const double2 *>(data + 4 * r0);
+            const double2 *d1 = reinterpret_cast<const double2 *>(data + 4 * r0 + 2 * deg);
+            for (int64_t kk = sub; kk < deg; kk += SPMV_LANES) {
+                const int c = node_idx[r0 + kk];
+                const double2 xv = *reinterpret_cast<const double2 *>(x + 2 * (int64_t)c);
+                const double2 v0 = d0[kk], v1 = d1[kk];
+                y0 = fma(v0.x, xv.x, y0); y0 = fma(v0.y, xv.y, y0);
+                y1 = fma(v1.x, xv.x, y1); y1 = fma(v1.y, xv.y, y1);
+            }
+        }
+#pragma unroll
+        for (int d = SPMV_LANES / 2; d; d >>= 1) {
+            y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+            y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+        }
+        if (a < n_node && sub == 0) {
+            if (fixed) {
+                if (fixed[2 * a]) y0 = 0.0;
+                if (fixed[2 * a + 1]) y1 = 0.0;
+            }
+            *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+            if (part_dot) {
+                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+            }
+        }
+    }
+    if (part_dot) {
+        const double s = block_sum(dot, sm);
+        if (threadIdx.x == 0) part_dot[blockIdx.x] = s;
+    }
+}
+
+// diagonal -> inverse (0 on fixed or empty rows)
+__global__ void k_diag_inv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
+                           const double *__restrict__ data, const uint8_t *__restrict__ fixed, double *__restrict__ dinv)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_node) return;
+    const int64_t r0 = node_ptr[a], deg = node_ptr[a + 1] - r0;
+    double dx = 0.0, dy = 0.0;
+    for (int64_t kk = 0; kk < deg; kk++)
+        if (node_idx[r0 + kk] == a) { dx = data[4 * r0 + 2 * kk]; dy = data[4 * r0 + 2 * deg + 2 * kk + 1]; break; }
+    dinv[2 * a] = (fixed[2 * a] || dx == 0.0) ? 0.0 : 1.0 / dx;
+    dinv[2 * a + 1] = (fixed[2 * a + 1] || dy == 0.0) ? 0.0 : 1.0 / dy;
+}
+
+// b = free ? f - y : 0 ; ufix = fixed ? value : 0 (pre-pass builds ufix)
+__global__ void k_build_ufix(int64_t n, const uint8_t *__restrict__ fixed, const double *__restrict__ val, double *__restrict__ ufix)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ufix[i] = fixed[i] ? val[i] : 0.0;
+}
+__global__ void k_build_rhs(int64_t n, const uint8_t *__restrict__ fixed, const double *__restrict__ f,
+                            const double *__restrict__ Kufix, double *__restrict__ b)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = fixed[i] ? 0.0 : f[i] - Kufix[i];
+}
+
+// scalars: sc[0..1] rz (double-buffered by iteration parity), sc[2] last rr, sc[3] bnorm2
+// init: x = 0, r = b, p = dinv*r ; partials of r.dinv.r and r.r
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ x,
+           double *__restrict__ r, double *__restrict__ p, double *__restrict__ part_rz, double *__restrict__ part_rr,
+           int keep_x)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = keep_x ? r[i] : b[i];
+        const double zi = dinv[i] * ri;
+        if (!keep_x) { x[i] = 0.0; r[i] = ri; }
+        p[i] = zi;
+        rz = fma(ri, zi, rz); rr = fma(ri, ri, rr);
+    }
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    if (threadIdx.x == 0) { part_rz[blockIdx.x] = s1; part_rr[blockIdx.x] = s2; }
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_init_scalars(const double *__restrict__ part_rz, const double *__restrict__ part_rr, int n_part, double *sc,
+                   int set_bnorm)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    const double rz = reduce_partials(part_rz, n_part, sm);
+    const double rr = reduce_partials(part_rr, n_part, sm);
+    if (threadIdx.x == 0) { sc[0] = rz; sc[1] = rz; sc[2] = rr; if (set_bnorm) sc[3] = rr; }
+}
+
+// x += alpha p ; r -= alpha q ; partials of r.dinv.r and r.r      (alpha = rz / p.q)
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_update(int64_t n, int it, const double *__restrict__ part_pq, int n_part_pq, const double *__restrict__ sc,
+             const double *__restrict__ p, const double *__restrict__ q, const double *__restrict__ dinv,
+             double *__restrict__ x, double *__restrict__ r, double *__restrict__ part_rz, double *__restrict__ part_rr)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    const double pq = reduce_partials(part_pq, n_part_pq, sm);
+    const double rz_old = sc[it & 1];
+    const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        const double zi = dinv[i] * ri;
+        rz = fma(ri, zi, rz); rr = fma(ri, ri, rr);
+    }
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    if (threadIdx.x == 0) { part_rz[blockIdx.x] = s1; part_rr[blockIdx.x] = s2; }
+}
+
+// p = dinv*r + beta p      (beta = rz_new / rz_old); block 0 publishes rz_new and rr
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_direction(int64_t n, int it, const double *__restrict__ part_rz, const double *__restrict__ part_rr, int n_part,
+                double *__restrict__ sc, const double *__restrict__ r, const double *__restrict__ dinv,
+                double *__restrict__ p, double *__restrict__ rr_hist)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    const double rz_new = reduce_partials(part_rz, n_part, sm);
+    const double rz_old = sc[it & 1];
+    const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    if (blockIdx.x == 0) {
+        const double rr = reduce_partials(part_rr, n_part, sm);
+        if (threadIdx.x == 0) { sc[(it + 1) & 1] = rz_new; sc[2] = rr; if (rr_hist) rr_hist[it] = rr; }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+// r = b - q (true residual), partial r.r
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_true_residual(int64_t n, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
+                double *__restrict__ part_rr)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    double rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        r[i] = ri;
+        rr = fma(ri, ri, rr);
+    }
+    const double s = block_sum(rr, sm);
+    if (threadIdx.x == 0) part_rr[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_reduce_to(const double *__restrict__ part, int n_part, double *out)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    const double s = reduce_partials(part, n_part, sm);
+    if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void k_add_vec(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
+cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, cudaStream_t s)
+{
+    const int64_t n_node = A.n / 2;
+    if (n_node == 0) return cudaSuccess;
+    const int64_t rows_per_block = VEC_BLOCK / SPMV_LANES;
+    int64_t grid = (n_node + rows_per_block - 1) / rows_per_block;
+    if (grid > 148 * 64) grid = 148 * 64;
+    k_spmv<<<(unsigned)grid, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, nullptr);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+static int vec_grid(int64_t n)
+{
+    int64_t g = (n + VEC_BLOCK - 1) / VEC_BLOCK;
+    if (g > 148 * 4) g = 148 * 4;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static int spmv_grid(int64_t n_node)
+{
+    const int64_t rows_per_block = VEC_BLOCK / SPMV_LANES;
+    int64_t g = (n_node + rows_per_block - 1) / rows_per_block;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
+                      PcgBuffers &w, cudaStream_t s, int64_t *launches)
+{
+    const int64_t n = A.n;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    k_build_ufix<<<g, 256, 0, s>>>(n, fixed, fixed_val, w.ufix);
+    cudaError_t e = spmv(A, w.ufix, w.q, nullptr, s);
+    if (e != cudaSuccess) return e;
+    k_build_rhs<<<g, 256, 0, s>>>(n, fixed, f, w.q, w.b);
+    k_diag_inv<<<(unsigned)((n / 2 + 255) / 256), 256, 0, s>>>(n / 2, A.node_ptr, A.node_idx, A.data, fixed, w.dinv);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+// Runs PCG; returns via info.  `chunk` iterations are enqueued between host residual checks.
+cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, double rtol, int maxit, int chunk,
+                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches)
+{
+    const int64_t n = A.n, n_node = n / 2;
+    const int gv = vec_grid(n), gs = spmv_grid(n_node);
+    cudaError_t e;
+    double sc_host[4];
+    k_pcg_init<<<gv, VEC_BLOCK, 0, s>>>(n, w.b, w.dinv, w.x, w.r, w.p, w.part_a, w.part_b, 0);
+    k_pcg_init_scalars<<<1, VEC_BLOCK, 0, s>>>(w.part_a, w.part_b, gv, w.sc, 1);
+    if (launches) *launches += 2;
+    e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 4, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    const double bnorm2 = sc_host[3];
+    info->iterations = 0; info->converged = 0; info->restarts = 0; info->relres_rec = 1.0; info->relres_true = 1.0;
+    if (bnorm2 == 0.0) {  // zero right-hand side: x = 0
+        info->converged = 1; info->relres_rec = 0.0; info->relres_true = 0.0;
+        return cudaSuccess;
+    }
+    const double tol2 = rtol * rtol * bnorm2;
+    int it = 0;       // global iteration counter (parity selects the rz buffer)
+    while (it < maxit) {
+        int todo = chunk;
+        if (it + todo > maxit) todo = maxit - it;
+        for (int k = 0; k < todo; k++, it++) {
+            k_spmv<<<gs, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c);
+            k_pcg_update<<<gv, VEC_BLOCK, 0, s>>>(n, it, w.part_c, gs, w.sc, w.p, w.q, w.dinv, w.x, w.r, w.part_a, w.part_b);
+            k_pcg_direction<<<gv, VEC_BLOCK, 0, s>>>(n, it, w.part_a, w.part_b, gv, w.sc, w.r, w.dinv, w.p, nullptr);
+        }
+        if (launches) *launches += 3 * (int64_t)todo;
+        e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 4, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        info->iterations = it;
+        info->relres_rec = sqrt(sc_host[2] / bnorm2);
+        if (!(sc_host[2] == sc_host[2])) break;  // NaN: breakdown
+        if (sc_host[2] <= tol2) {
+            // recurrence residual says converged: verify with the true residual r = b - A x
+            k_spmv<<<gs, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.x, w.q, fixed, nullptr);
+            k_true_residual<<<gv, VEC_BLOCK, 0, s>>>(n, w.b, w.q, w.r, w.part_b);
+            k_reduce_to<<<1, VEC_BLOCK, 0, s>>>(w.part_b, gv, w.sc + 4);
+            if (launches) *launches += 3;
+            double rr_true;
+            e = cudaMemcpyAsync(&rr_true, w.sc + 4, sizeof(double), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return e;
+            info->relres_true = sqrt(rr_true / bnorm2);
+            if (rr_true <= tol2) { info->converged = 1; return cudaSuccess; }
+            // drift: restart from the true residual (x kept), direction reset
+            info->restarts++;
+            if (info->restarts > 20) break;
+            k_pcg_init<<<gv, VEC_BLOCK, 0, s>>>(n, w.b, w.dinv, w.x, w.r, w.p, w.part_a, w.part_b, 1);
+            k_pcg_init_scalars<<<1, VEC_BLOCK, 0, s>>>(w.part_a, w.part_b, gv, w.sc, 0);
+            if (launches) *launches += 2;
+        }
+    }
+    // not converged by the recurrence test: report the true residual anyway
+    k_spmv<<<gs, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.x, w.q, fixed, nullptr);
+    k_true_residual<<<gv, VEC_BLOCK, 0, s>>>(n, w.b, w.q, w.r, w.part_b);
+    k_reduce_to<<<1, VEC_BLOCK, 0, s>>>(w.part_b, gv, w.sc + 4);
+    if (launches) *launches += 3;
+    double rr_true;
+    e = cudaMemcpyAsync(&rr_true, w.sc + 4, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    info->relres_true = sqrt(rr_true / bnorm2);
+    info->converged = rr_true <= tol2 ? 1 : 0;
+    return cudaGetLastError();
+}
+
+cudaError_t pcg_finish(int64_t n, PcgBuffers &w, double *u_dev, cudaStream_t s)
+{
+    k_add_vec<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, w.x, w.ufix, u_dev);
+    return cudaGetLastError();
+}
+
+// 0.5 u^T K u
+cudaError_t energy_of(const DevSystem &A, const double *u, double *q_tmp, double *part, double *out_dev, cudaStream_t s)
+{
+    const int64_t n_node = A.n / 2;
+    const int gs = spmv_grid(n_node);
+    k_spmv<<<gs, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, u, q_tmp, nullptr, part);
+    k_reduce_to<<<1, VEC_BLOCK, 0, s>>>(part, gs, out_dev);
+    return cudaGetLastError();
+}
+
+}  // namespace mofem
