@@ -88,7 +88,8 @@ typedef struct {
 
 typedef struct {
     int32_t iterations;
-    int32_t converged;
+    int32_t converged;    /* 0 no; 1 true residual <= rtol; 2 recurrence residual <= rtol and the true residual
+                             stagnated at the fp64 attainable accuracy (reported in relres_true) */
     double relres_true;   /* ||b-Ax|| / ||b|| recomputed at exit */
     double relres_rec;    /* recurrence residual at exit */
     int32_t restarts;     /* times the true residual replaced the recurrence residual */

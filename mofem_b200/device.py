@@ -135,7 +135,7 @@ class Context:
         u = np.empty(self.n_dof, np.float64) if out is None else out
         si = _lib.MofemSolveInfo()
         rc = self._L.mofem_solve(self._h, float(rtol), int(maxit), _lib.ptr(u), C.byref(si))
-        info = dict(iterations=si.iterations, converged=bool(si.converged), relres_true=si.relres_true,
+        info = dict(iterations=si.iterations, converged=int(si.converged), relres_true=si.relres_true,
                     relres_rec=si.relres_rec, restarts=si.restarts)
         if rc == _lib.E_NOCONV and not check:
             return u, info
@@ -167,7 +167,7 @@ class Context:
         self._keep = keep
         self.n_dof = 2 * int(s.n_node)
         self._ck(rc)
-        return u, e.value, dict(iterations=si.iterations, converged=bool(si.converged), relres_true=si.relres_true,
+        return u, e.value, dict(iterations=si.iterations, converged=int(si.converged), relres_true=si.relres_true,
                                 relres_rec=si.relres_rec, restarts=si.restarts)
 
     def timing(self) -> dict:
