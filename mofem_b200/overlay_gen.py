@@ -1,0 +1,371 @@
+"""Synthetic overlapping-mesh problems emitted directly as flattened SoA (the reference ships no generator).
+
+Patch family ``P(p=5, period=8)`` of SURVEY.md App. C: mesh 0 is an ``n0 x n0`` quad4 grid on the unit square,
+mesh 1 is ``(n0/8)^2`` disjoint patches of ``5 x 5`` quad4 elements with the same spacing, lower-left corner of
+patch ``(a, b)`` at ``((8a+1.37)h, (8b+1.41)h)``; seeded jitter moves mesh-0 interior nodes and patch-interior
+nodes (patch borders stay straight), so the quads are non-affine and the Newton inverse map needs 3-4 updates.
+
+The generator follows the reference's rules for what the plane sweep would hand to the solver:
+
+* overlay cells = pieces with a constant tuple of incident elements (computGeometry/planeSweepMeshes.py:354);
+  every mesh-1 element contains exactly one mesh-0 node and is cut into 4 convex 4-gons; the patch border cuts
+  the surrounding ring of mesh-0 elements into one-element cells (5-gons on the sides, L-shaped 6-gons at the
+  corners); untouched mesh-0 elements are regular quadFE cells;
+* triangulation = the reference's recursive "cut at the up-left-most vertex" rule
+  (computGeometry/triangulation.py:49-139), triangles in the same order and vertex rotation;
+* node weights: 0 on patch-border nodes (a mesh boundary strictly inside the domain), 1 elsewhere
+  (planeSweepMeshes.py:434-446); ``rho_j(v) = c_j sum_a N_a(xi_j(v)) w_a / sum_k (...)``, ``c_0 = 1``,
+  ``c_{j>=1} = 9`` (planeSweepMeshes.py:1004-1027).
+
+:func:`patch_deck` returns the same problem as a reference ``inputData`` tuple so that small sizes can be pushed
+through the reference's own sweep for cross-validation (tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .flatten import CELL_OVERLAY, CELL_REGULAR, SOLVER_LOWER, FlatProblem, material_matrix
+
+PERIOD = 8
+PATCH = 5
+OFF_X, OFF_Y = 1.37, 1.41
+SEED = 20260101
+
+
+@dataclass
+class PatchMeshes:
+    n0: int
+    P: int                    # patches per direction
+    X0: np.ndarray            # [n0+1, n0+1, 2] mesh-0 node coordinates, indexed [j, i]
+    X1: np.ndarray            # [P, P, 6, 6, 2] mesh-1 node coordinates, indexed [b, a, t, s]
+
+    @property
+    def n_node0(self): return (self.n0 + 1) ** 2
+    @property
+    def n_elem0(self): return self.n0 ** 2
+    @property
+    def n_node(self): return self.n_node0 + 36 * self.P ** 2
+    @property
+    def n_elem(self): return self.n_elem0 + 25 * self.P ** 2
+
+    def node_xy(self):
+        return np.concatenate([self.X0.reshape(-1, 2), self.X1.reshape(-1, 2)])
+
+    def elem_nodes0(self):
+        n0 = self.n0
+        j, i = np.meshgrid(np.arange(n0), np.arange(n0), indexing="ij")
+        q = (j * (n0 + 1) + i).reshape(-1)
+        return np.stack([q, q + 1, q + n0 + 2, q + n0 + 1], 1)
+
+    def elem_nodes1(self):
+        P = self.P
+        base = self.n_node0 + 36 * np.arange(P * P)
+        t, s = np.meshgrid(np.arange(5), np.arange(5), indexing="ij")
+        loc = (6 * t + s).reshape(-1)
+        e = np.stack([loc, loc + 1, loc + 7, loc + 6], 1)             # [25, 4]
+        return (base[:, None, None] + e[None]).reshape(-1, 4)
+
+
+def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED) -> PatchMeshes:
+    if n0 % PERIOD or n0 < PERIOD:
+        raise ValueError("n0 must be a positive multiple of 8")
+    h = 1.0 / n0
+    P = n0 // PERIOD
+    rng = np.random.default_rng(seed)
+    j, i = np.meshgrid(np.arange(n0 + 1), np.arange(n0 + 1), indexing="ij")
+    X0 = np.stack([i, j], -1).astype(np.float64)
+    jit0 = rng.uniform(-jitter, jitter, X0.shape)
+    jit0[0, :] = jit0[-1, :] = 0.0
+    jit0[:, 0] = jit0[:, -1] = 0.0
+    X0 = (X0 + jit0) * h
+    b, a, t, s = np.meshgrid(np.arange(P), np.arange(P), np.arange(6), np.arange(6), indexing="ij")
+    X1 = np.stack([PERIOD * a + OFF_X + s, PERIOD * b + OFF_Y + t], -1).astype(np.float64)
+    jit1 = rng.uniform(-jitter, jitter, X1.shape)
+    jit1[:, :, 0, :] = jit1[:, :, 5, :] = 0.0
+    jit1[:, :, :, 0] = jit1[:, :, :, 5] = 0.0
+    X1 = (X1 + jit1) * h
+    return PatchMeshes(n0=n0, P=P, X0=X0, X1=X1)
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry helpers (vectorised over the leading axes)
+# ---------------------------------------------------------------------------------------------
+def _intersect(p, q, c, d):
+    """Intersection of segment p-q with the line through c-d."""
+    r = q - p
+    e = d - c
+    den = r[..., 0] * e[..., 1] - r[..., 1] * e[..., 0]
+    t = ((c[..., 0] - p[..., 0]) * e[..., 1] - (c[..., 1] - p[..., 1]) * e[..., 0]) / den
+    return p + t[..., None] * r
+
+
+def _quad_shape(r, s):
+    N = 0.25 * np.stack([(1 - r) * (1 - s), (1 + r) * (1 - s), (1 + r) * (1 + s), (1 - r) * (1 + s)], -1)
+    dr = 0.25 * np.stack([-(1 - s), (1 - s), (1 + s), -(1 + s)], -1)
+    ds = 0.25 * np.stack([-(1 - r), -(1 + r), (1 + r), (1 - r)], -1)
+    return N, dr, ds
+
+
+def _inv_quad_N(coord, xy, iters=8):
+    """Shape-function values N_a(xi(xy)) of quad4 elements (Newton inverse map, invShapeFunction.py:41-73)."""
+    c0 = coord[..., :1, :]
+    cn = coord - c0
+    x = xy - c0[..., 0, :]
+    r = np.zeros(xy.shape[:-1]); s = np.zeros(xy.shape[:-1])
+    for _ in range(iters):
+        N, dr, ds = _quad_shape(r, s)
+        res = x - np.einsum("...a,...ad->...d", N, cn)
+        j00 = np.einsum("...a,...a->...", dr, cn[..., 0]); j01 = np.einsum("...a,...a->...", ds, cn[..., 0])
+        j10 = np.einsum("...a,...a->...", dr, cn[..., 1]); j11 = np.einsum("...a,...a->...", ds, cn[..., 1])
+        det = j00 * j11 - j01 * j10
+        r = r + (res[..., 0] * j11 - res[..., 1] * j01) / det
+        s = s + (-res[..., 0] * j10 + res[..., 1] * j00) / det
+    return _quad_shape(r, s)[0]
+
+
+def _point_gt(a, b):
+    """point_2D.__gt__ (planeSweepMeshes.py:36-40): higher y first, then smaller x."""
+    return a[1] > b[1] if a[1] != b[1] else a[0] < b[0]
+
+
+def _is_left(p1, p2, p3):
+    return ((p2[0] - p1[0]) * (p3[1] - p1[1]) - (p2[1] - p1[1]) * (p3[0] - p1[0])) / math.sqrt(
+        (p2[1] - p1[1]) ** 2 + (p2[0] - p1[0]) ** 2)
+
+
+def _in_polygon(pt, poly):
+    """triangulation.isInPolygon:151-171 (winding number; boundary counts as inside)."""
+    w = 0
+    for i in range(len(poly) - 1):
+        a, b = poly[i], poly[i + 1]
+        if (a[0] == pt[0] and a[1] == pt[1]) or (b[0] == pt[0] and b[1] == pt[1]):
+            return 1
+        if a[1] == pt[1] == b[1] and (pt[0] - a[0]) * (pt[0] - b[0]) <= 0:
+            return 1
+        if a[1] <= pt[1]:
+            if b[1] > pt[1]:
+                v = _is_left(a, b, pt)
+                if v > 0: w += 1
+                if v == 0: return 1
+        elif b[1] <= pt[1]:
+            v = _is_left(a, b, pt)
+            if v < 0: w -= 1
+            if v == 0: return 1
+    return w
+
+
+def ear_triangulate(pts, ids=None):
+    """The reference's ``simpleTriangulation`` (triangulation.py:49-139) on a CCW vertex list.
+
+    ``pts``: sequence of (x, y); ``ids``: vertex labels (default 0..n-1), ``ids[0]`` is the origin of the
+    half-edge the recursion starts from.  Returns triangles as label triples, in the reference's order and
+    vertex rotation."""
+    if ids is None:
+        ids = list(range(len(pts)))
+    n = len(ids)
+    if n == 3:
+        return [tuple(ids)]
+    u = 0
+    for k in range(1, n):
+        if _point_gt(pts[ids[k]], pts[ids[u]]):
+            u = k
+    ring = ids[u:] + ids[:u]                       # ring[0] = up-left-most vertex U
+    U, nxt, prv = ring[0], ring[1], ring[-1]
+    tri = [pts[U], pts[nxt], pts[prv], pts[U]]
+    inside, dist = [], []
+    for k in range(2, n - 1):
+        if _in_polygon(pts[ring[k]], tri):
+            inside.append(k)
+            dist.append(_is_left(pts[nxt], pts[prv], pts[ring[k]]))
+    if not inside:
+        t1 = [(prv, U, nxt)]                        # simpleTriangulation(edge1, 3), edge1 = U.prev
+        t2 = ear_triangulate(pts, ring[1:])         # start edge2 = U.next
+    else:
+        best = 0                                    # the reference keeps the FIRST maximum (strict >)
+        for m in range(1, len(dist)):
+            if dist[m] > dist[best]:
+                best = m
+        k = inside[best]
+        t1 = ear_triangulate(pts, ring[:k + 1])     # U ... X, start edge1 = U
+        t2 = ear_triangulate(pts, ring[k:] + [U])   # X ... U, start edge2 = X
+    return t2 + t1
+
+
+# ---------------------------------------------------------------------------------------------
+# the flattened problem
+# ---------------------------------------------------------------------------------------------
+def _quad_triangles(poly):
+    """Vectorised ``ear_triangulate`` for convex 4-gons: poly [n,4,2] -> vertex index table [n,2,3]."""
+    y = poly[..., 1]; x = poly[..., 0]
+    ymax = y.max(1, keepdims=True)
+    cand = np.where(y == ymax, x, np.inf)
+    u = cand.argmin(1)                                # max y, then min x
+    # triangles: (U.next, opposite, U.prev) then (U.prev, U, U.next)
+    idx = np.stack([np.stack([u + 1, u + 2, u + 3], 1), np.stack([u + 3, u, u + 1], 1)], 1) % 4
+    return idx
+
+
+def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
+                 solver: int = SOLVER_LOWER, return_meshes: bool = False):
+    """Flattened 2-mesh patch-family problem + its linear system.
+
+    Returns ``(FlatProblem, rhs, fixed, fixed_value)``: left edge of mesh 0 clamped, concentrated load
+    ``(1, -0.5)`` at the bottom-right corner node of mesh 0."""
+    pm = patch_meshes(n0, jitter, seed)
+    P = pm.P
+    X0, X1 = pm.X0, pm.X1
+    n_elem0 = pm.n_elem0
+    node0 = lambda j, i: j * (n0 + 1) + i
+    elem0 = lambda j, i: j * n0 + i
+
+    b, a, q, p = np.meshgrid(np.arange(P), np.arange(P), np.arange(5), np.arange(5), indexing="ij")
+    C00 = X1[b, a, q, p]; C10 = X1[b, a, q, p + 1]; C11 = X1[b, a, q + 1, p + 1]; C01 = X1[b, a, q + 1, p]
+    ip = PERIOD * a + 2 + p
+    jp = PERIOD * b + 2 + q
+    Pn = X0[jp, ip]
+    IW = _intersect(Pn, X0[jp, ip - 1], C00, C01)
+    IE = _intersect(Pn, X0[jp, ip + 1], C10, C11)
+    IS = _intersect(Pn, X0[jp - 1, ip], C00, C10)
+    IN = _intersect(Pn, X0[jp + 1, ip], C01, C11)
+    # straight patch borders: pin the border coordinate exactly
+    IW[:, :, :, 0, 0] = X1[:, :, 0:1, 0, 0]
+    IE[:, :, :, 4, 0] = X1[:, :, 0:1, 5, 0]
+    IS[:, :, 0, :, 1] = X1[:, :, 0, 0:1, 1]
+    IN[:, :, 4, :, 1] = X1[:, :, 5, 0:1, 1]
+
+    # ---- two-element cells: 4 pieces per mesh-1 element ------------------------------------
+    pieces = np.stack([
+        np.stack([C00, IS, Pn, IW], -2),     # lower-left  (dx, dy) = (0, 0)
+        np.stack([IS, C10, IE, Pn], -2),     # lower-right (1, 0)
+        np.stack([Pn, IE, C11, IN], -2),     # upper-right (1, 1)
+        np.stack([IW, Pn, IN, C01], -2),     # upper-left  (0, 1)
+    ], 4)                                     # [P,P,5,5,4 pieces,4 verts,2]
+    dxy = np.array([[0, 0], [1, 0], [1, 1], [0, 1]])
+    e0_piece = elem0((jp - 1)[..., None] + dxy[:, 1], (ip - 1)[..., None] + dxy[:, 0])        # [P,P,5,5,4]
+    e1_piece = np.broadcast_to((n_elem0 + 25 * (b * P + a) + 5 * q + p)[..., None], e0_piece.shape)
+    pieces = pieces.reshape(-1, 4, 2)
+    e0_piece = e0_piece.reshape(-1); e1_piece = e1_piece.reshape(-1)
+    n_piece = pieces.shape[0]
+
+    en0 = pm.elem_nodes0(); en1 = pm.elem_nodes1()
+    node_xy = pm.node_xy()
+    w1 = np.zeros((6, 6)); w1[1:5, 1:5] = 1.0
+    node_w = np.concatenate([np.ones(pm.n_node0), np.tile(w1.reshape(-1), P * P)])
+
+    c0 = node_xy[en0[e0_piece]]                                   # [n_piece,4,2]
+    c1 = node_xy[en1[e1_piece - n_elem0]]
+    wgt1 = node_w[en1[e1_piece - n_elem0]]                        # [n_piece,4]
+    rho_piece = np.empty((n_piece, 4, 2))
+    for v in range(4):
+        N0 = _inv_quad_N(c0, pieces[:, v])
+        N1 = _inv_quad_N(c1, pieces[:, v])
+        r0 = N0.sum(-1)                                           # weights of mesh 0 are all 1
+        r1 = 9.0 * (N1 * wgt1).sum(-1)
+        rho_piece[:, v, 0] = r0 / (r0 + r1)
+        rho_piece[:, v, 1] = r1 / (r0 + r1)
+    tri_idx = _quad_triangles(pieces)                             # [n_piece,2,3]
+    ar = np.arange(n_piece)[:, None, None]
+    piece_tri_xy = pieces[ar, tri_idx]                            # [n_piece,2,3,2]
+    piece_tri_rho = rho_piece[ar, tri_idx]                        # [n_piece,2,3,2]
+
+    # ---- ring cells (one element, triangulated) -----------------------------------------------
+    ring_elem, ring_tri_xy, ring_ptr = [], [], [0]
+    X0l = X0.tolist()
+    for bb in range(P):
+        for aa in range(P):
+            iw = IW[bb, aa, :, 0].tolist(); ie = IE[bb, aa, :, 4].tolist()
+            is_ = IS[bb, aa, 0, :].tolist(); in_ = IN[bb, aa, 4, :].tolist()
+            m = X1[bb, aa].tolist()
+            i1, j1 = PERIOD * aa + 1, PERIOD * bb + 1
+            polys = []
+
+            def corners(u, v):
+                i, j = i1 + u, j1 + v
+                return X0l[j][i], X0l[j][i + 1], X0l[j + 1][i + 1], X0l[j + 1][i]
+            for v in range(1, 5):      # left and right sides
+                n00, n10, n11, n01 = corners(0, v)
+                polys.append((0, v, [n00, iw[v - 1], m[v][0], iw[v], n01]))
+                n00, n10, n11, n01 = corners(5, v)
+                polys.append((5, v, [ie[v - 1], n10, n11, ie[v], m[v][5]]))
+            for u in range(1, 5):      # bottom and top sides
+                n00, n10, n11, n01 = corners(u, 0)
+                polys.append((u, 0, [n00, n10, is_[u], m[0][u], is_[u - 1]]))
+                n00, n10, n11, n01 = corners(u, 5)
+                polys.append((u, 5, [in_[u - 1], m[5][u], in_[u], n11, n01]))
+            n00, n10, n11, n01 = corners(0, 0)
+            polys.append((0, 0, [n00, n10, is_[0], m[0][0], iw[0], n01]))
+            n00, n10, n11, n01 = corners(5, 0)
+            polys.append((5, 0, [n00, n10, n11, ie[0], m[0][5], is_[4]]))
+            n00, n10, n11, n01 = corners(5, 5)
+            polys.append((5, 5, [ie[4], n10, n11, n01, in_[4], m[5][5]]))
+            n00, n10, n11, n01 = corners(0, 5)
+            polys.append((0, 5, [n00, iw[4], m[5][0], in_[0], n11, n01]))
+            for u, v, poly in polys:
+                tris = ear_triangulate(poly)
+                ring_elem.append(elem0(j1 + v, i1 + u))
+                for t in tris:
+                    ring_tri_xy.append([poly[t[0]], poly[t[1]], poly[t[2]]])
+                ring_ptr.append(len(ring_tri_xy))
+    ring_elem = np.array(ring_elem, dtype=np.int64)
+    ring_tri_xy = np.array(ring_tri_xy, dtype=np.float64).reshape(-1, 3, 2)
+    n_ring = len(ring_elem)
+
+    # ---- untouched mesh-0 elements -> regular quadFE cells ------------------------------------------
+    touched = np.zeros((n0, n0), dtype=bool)
+    for d in range(6):
+        for e in range(6):
+            touched[(PERIOD * np.arange(P) + 1 + d)[:, None], (PERIOD * np.arange(P) + 1 + e)[None, :]] = True
+    reg_elem = np.flatnonzero(~touched.reshape(-1))
+    n_reg = len(reg_elem)
+
+    # ---- assemble the SoA ----------------------------------------------------------------------------
+    C = n_reg + n_ring + n_piece
+    cell_elem = np.full((C, 2), -1, dtype=np.int32)
+    cell_kind = np.zeros(C, dtype=np.int32)
+    cell_elem[:n_reg, 0] = reg_elem
+    cell_elem[n_reg:n_reg + n_ring, 0] = ring_elem
+    cell_kind[n_reg:] = CELL_OVERLAY
+    cell_elem[n_reg + n_ring:, 0] = e0_piece
+    cell_elem[n_reg + n_ring:, 1] = e1_piece
+    ntri = np.zeros(C, dtype=np.int64)
+    ntri[n_reg:n_reg + n_ring] = np.diff(np.array(ring_ptr))
+    ntri[n_reg + n_ring:] = 2
+    tri_ptr = np.concatenate([[0], np.cumsum(ntri)])
+    ring_rho = np.zeros((len(ring_tri_xy), 3, 2)); ring_rho[:, :, 0] = 1.0
+    tri_xy = np.concatenate([ring_tri_xy, piece_tri_xy.reshape(-1, 3, 2)])
+    tri_rho = np.concatenate([ring_rho, piece_tri_rho.reshape(-1, 3, 2)])
+
+    elem_nodes = np.full((pm.n_elem, 9), -1, dtype=np.int32)
+    elem_nodes[:n_elem0, :4] = en0
+    elem_nodes[n_elem0:, :4] = en1
+    fp = FlatProblem(
+        solver=int(solver), n_mesh=2, node_xy=np.ascontiguousarray(node_xy), elem_nodes=elem_nodes,
+        elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
+        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.ones(25 * P * P, np.int32)]),
+        mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), cell_elem=cell_elem, cell_kind=cell_kind,
+        cell_tri_ptr=tri_ptr.astype(np.int64), tri_xy=np.ascontiguousarray(tri_xy),
+        tri_rho=np.ascontiguousarray(tri_rho), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem])
+
+    n_dof = 2 * pm.n_node
+    fixed = np.zeros(n_dof, dtype=np.uint8)
+    left = node0(np.arange(n0 + 1), 0)
+    fixed[2 * left] = 1; fixed[2 * left + 1] = 1
+    rhs = np.zeros(n_dof)
+    rhs[2 * n0] = 1.0; rhs[2 * n0 + 1] = -0.5
+    out = (fp, rhs, fixed, np.zeros(n_dof))
+    return out + (pm,) if return_meshes else out
+
+
+def patch_deck(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3, solver: int = 1):
+    """The same problem as a reference ``inputData`` tuple (inputFunctions/inputF.py:204-205, concentrated-force
+    form), for pushing small sizes through the reference's own plane sweep."""
+    pm = patch_meshes(n0, jitter, seed)
+    coords = pm.node_xy().tolist()
+    meshes = [pm.elem_nodes0().tolist(), pm.elem_nodes1().tolist()]
+    material_mesh = [[0] * len(meshes[0]), [0] * len(meshes[1])]
+    constraints = [[j * (n0 + 1), 1, 1, 0.0, 0.0] for j in range(n0 + 1)]
+    forces = [[], [[n0, 1.0, -0.5]]]
+    return ([solver, 1], None, None, meshes, material_mesh, coords, [[E, nu]], constraints, [0, 0, 1], forces)

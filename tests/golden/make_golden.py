@@ -15,6 +15,8 @@ Fixtures written (npz, float64 / int32):
       hooking scipy.sparse.coo_matrix and spsolve inside linearSolvers/AMORE.py.
   single_*.npz  -- traditionalElement.{lowerOrderFE,quadraticFE,ICMFE} on small
       single-mesh decks generated here.
+  patch16.npz -- the synthetic patch family (n0=16, jittered) as a reference deck pushed through the
+      reference's plane sweep + AMORE.lowerOrderAMORE: pins mofem_b200/overlay_gen.py.
   zoo_s{1,2,3}.npz -- array level: synthetic all-types problems pushed through
       stiffnessMatrix.{lowerOrderAMORE,quadraticAMORE,triFE,...} following the
       reference's cell loop.
@@ -162,8 +164,9 @@ def pack(fp, I, J, V, extra=None):
     return d
 
 
-def run_amore(stem):
-    input_data = inputF.txtInput(stem)
+def run_amore(stem, input_data=None):
+    if input_data is None:
+        input_data = inputF.txtInput(stem)
     solver = input_data[0][0]
     with contextlib.redirect_stdout(io.StringIO()):
         overlapping_mesh, polygons, nep = overlay(input_data)
@@ -311,6 +314,11 @@ def main():
     for stem in ("simpleOFE3", "AMOREBracket"):
         d, _ = run_amore(stem)
         np.savez_compressed(os.path.join(HERE, stem + ".npz"), **d)
+    # synthetic patch family (mofem_b200/overlay_gen.py) pushed through the reference's own plane sweep
+    from mofem_b200 import overlay_gen
+    planeSweepMeshes.scale = [1, 1]
+    d, _ = run_amore("patch16", overlay_gen.patch_deck(16))
+    np.savez_compressed(os.path.join(HERE, "patch16.npz"), **d)
     for kind in ("lower", "icm", "quad"):
         np.savez_compressed(os.path.join(HERE, f"single_{kind}.npz"), **run_single(kind))
     for solver in (1, 2, 3):
