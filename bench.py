@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of junbinhuang/MOFEM on B200: overlay-cell stiffness assembly + the linear solve.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, through the C-ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm on the host cores
+
+Workload (BASELINE.json configs[2]): synthetic 2-mesh patch-family overlay,
+n0 = 664 -> 1.02 M cells, 1.82 M integration triangles, 1.38 M DOF, 2.0e8 COO triplets, 5.0e7 CSR non-zeros.
+One *step* = one full pass of the hot path over that problem: CSR symbolic phase + fp64 integration of every
+block + deterministic reduce into CSR values + constraint elimination + Jacobi-PCG to a true relative residual
+of 1e-10 + energy.  ``value`` = overlay cells / step time (inputs resident in HBM); ``ms_per_step`` is the
+K-assembly + solve wall time; ``e2e`` is the same through ``Context.assemble_solve`` with pinned HOST buffers
+(host->device copies of the flattened problem and device->host copy of the displacement inside the timed region).
+The plane sweep / generator that produces the flattened overlay is untimed preprocessing (reported in ``prep_s``).
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "overlay-cell stiffness assembly cells/s (fp64) and K-assembly+solve wall time"
+UNIT = "cells/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(info, n_dof):
+    """Per-launch algorithmic bytes of the HBM-bound kernels (DESIGN.md 'Kernels and rooflines')."""
+    nnz = info["nnz"]
+    n_node = n_dof // 2
+    n_pair = info["n_pair"]
+    n_contrib = info["n_coo"] // 4
+    return {
+        # block CSR as stored: 8 B per value + one 4 B column index per 2x2 block + node_ptr + x, y + fixed mask
+        "spmv": 8 * nnz + nnz + 8 * (n_node + 1) + 8 * n_dof + 8 * n_dof + n_dof,
+        # SURVEY.md section 8d scalar-CSR figure for the same product (12 B per stored entry)
+        "spmv_scalar_csr": 12 * nnz + 4 * (n_dof + 1) + 16 * n_dof,
+        "update": 8 * n_dof * 7,         # reads p, q, x, r, dinv; writes x, r
+        "direction": 8 * n_dof * 4,      # reads r, dinv, p; writes p
+        # numeric reduce: every block value once (32 B per node pair), its 4 B source slot, CSR values out
+        "numeric": 32 * n_pair + 4 * n_contrib + 8 * nnz,
+    }
+
+
+def run_reference(args):
+    """The reference's CPU algorithm (oracle port, all host threads) + scipy coo->csr + spsolve, on a bounded sample."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from mofem_b200.overlay_gen import patch_family
+    from oracle import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n0 = args.ref_n0
+    fp, rhs, fixed, val = patch_family(n0)
+    free = fixed == 0
+
+    def step():
+        I, J, V, _, _ = oracle.assemble_coo(fp, cores)
+        K = sp.coo_matrix((V, (I, J)), shape=(fp.n_dof,) * 2).tocsr()
+        b = (rhs - K @ val)[free]
+        Kff = K[free][:, free].tocsc()
+        x = spla.spsolve(Kff, b)
+        u = val.copy(); u[free] = x
+        return 0.5 * u @ (K @ u)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = fp.n_cell / dt
+    sample = (f"patch family n0={n0} ({fp.n_cell} cells, {fp.n_dof} DOF): oracle C port of the reference's assembly "
+              f"on {cores} threads + scipy coo->csr + constraint elimination + spsolve (the reference's own solver)")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "syn-1M patch-family overlay (2 meshes, quad4/quad4), bounded sample", "n0": n0,
+                      "cells": fp.n_cell, "dof": fp.n_dof},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(n0, budget_cells=None):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from mofem_b200.overlay_gen import patch_family
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    fp, rhs, fixed, val = patch_family(n0)
+    free = fixed == 0
+    t0 = time.perf_counter()
+    I, J, V, _, _ = oracle.assemble_coo(fp, cores)
+    t1 = time.perf_counter()
+    K = sp.coo_matrix((V, (I, J)), shape=(fp.n_dof,) * 2).tocsr()
+    t2 = time.perf_counter()
+    b = (rhs - K @ val)[free]
+    x = spla.spsolve(K[free][:, free].tocsc(), b)
+    t3 = time.perf_counter()
+    return {"value": fp.n_cell / (t3 - t0), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"patch family n0={n0}: {fp.n_cell} cells, {fp.n_dof} DOF (same family as the workload)",
+            "assembly_cells_per_s": fp.n_cell / (t1 - t0), "coo_to_csr_s": t2 - t1, "spsolve_s": t3 - t2,
+            "note": "oracle = C port of the reference's NumPy arithmetic; the reference's own Python runs at "
+                    "~120-340 cells/s on one thread (BASELINE.md)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n0", type=int, default=664, help="mesh-0 elements per side (664 -> ~1M overlay cells)")
+    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--ref-n0", type=int, default=256, help="size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events inside the PCG loop")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mofem_b200.device import Context
+    from mofem_b200.flatten import FlatProblem
+    from mofem_b200.overlay_gen import patch_family
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (mofem_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # ---- untimed preprocessing: the flattened overlay (what the plane sweep + flatten() hand to the solver) ------
+    t0 = time.perf_counter()
+    fp, rhs, fixed, val = patch_family(args.n0, seed=20260101 + rank)
+    prep_s = time.perf_counter() - t0
+    log(f"[rank {rank}] generated n0={args.n0}: {fp.n_cell} cells, {fp.n_tri} triangles, {fp.n_dof} DOF in {prep_s:.1f}s")
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    host = {k: pinned(getattr(fp, k)) for k in FlatProblem.ARRAYS if getattr(fp, k) is not None and k != "elem_mesh"}
+    host_sys = {"rhs": pinned(rhs), "fixed": pinned(fixed), "val": pinned(val)}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values()) + \
+        sum(t.numel() * t.element_size() for t in host_sys.values())
+    d2h_bytes = 8 * fp.n_dof + 8
+
+    import copy
+    fp_host = copy.copy(fp)
+    for k, t in host.items():
+        setattr(fp_host, k, t.numpy())
+    fp_dev = copy.copy(fp)
+    for k, t in host.items():
+        setattr(fp_dev, k, t.to(dev))
+    rhs_d, fixed_d, val_d = (host_sys[k].to(dev) for k in ("rhs", "fixed", "val"))
+    u_d = torch.empty(fp.n_dof, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    ctx = Context(local)
+    ctx.set_profile(not args.no_profile)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    maxit = 400000
+    last = {}
+
+    def step_resident():
+        ctx.set_problem(fp_dev).symbolic().assemble()
+        ctx.set_system(rhs_d, fixed_d, val_d)
+        _, si = ctx.solve(rtol=args.rtol, maxit=maxit, out=u_d)
+        last["solve"] = si
+        last["energy"] = ctx.energy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    phases = {"symbolic_ms": 0.0, "integrate_ms": 0.0, "numeric_ms": 0.0, "solve_ms": 0.0}
+    prof = {"spmv_ms": 0.0, "update_ms": 0.0, "direction_ms": 0.0, "iterations": 0}
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        tm = ctx.timing()
+        for k in phases:
+            phases[k] += tm[k]
+        launches += sum(tm["launches"].values()) + 2    # + energy SpMV and its reduction
+        pp = ctx.pcg_profile()
+        for k in prof:
+            prof[k] += pp[k]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+    if world > 1:
+        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    info = ctx.info()
+    si = last["solve"]
+
+    # ---- end to end through the public API with pinned host buffers -----------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        u_h, energy_h, si_h = ctx.assemble_solve(fp_host, host_sys["rhs"].numpy(), host_sys["fixed"].numpy(),
+                                                 host_sys["val"].numpy(), rtol=args.rtol, maxit=maxit)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.array_equal(u_h, u_d.cpu().numpy()), "host-buffer path and resident path must give identical bits"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    ab = algorithmic_bytes(info, fp.n_dof)
+    iters = max(prof["iterations"], 1)
+    spmv_ms = prof["spmv_ms"] / iters if prof["iterations"] else None
+    roofline = None
+    if spmv_ms:
+        ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
+        roofline = {"kernel": "k_spmv (block-CSR SpMV inside Jacobi-PCG)", "bound": "hbm", "achieved": ach,
+                    "peak": peaks["hbm_gbs"], "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes_per_launch": ab["spmv"], "avg_launch_ms": spmv_ms,
+                    "scalar_csr_equivalent_gbs": ab["spmv_scalar_csr"] / (spmv_ms * 1e-3) / 1e9,
+                    "share_of_step": prof["spmv_ms"] / args.steps / step_ms}
+    kernels = {}
+    if prof["iterations"]:
+        for name in ("update", "direction"):
+            ms = prof[name + "_ms"] / iters
+            kernels["k_pcg_" + name] = {"avg_launch_ms": ms, "gbs": ab[name] / (ms * 1e-3) / 1e9,
+                                        "frac_hbm": ab[name] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    nm = phases["numeric_ms"] / args.steps
+    kernels["k_numeric"] = {"avg_launch_ms": nm, "gbs": ab["numeric"] / (nm * 1e-3) / 1e9,
+                            "frac_hbm": ab["numeric"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    im = phases["integrate_ms"] / args.steps
+    kernels["integrate (all classes)"] = {"ms": im, "cells_per_s": fp.n_cell / (im * 1e-3),
+                                          "newton_updates": info["newton_updates"], "evaluations": info["n_eval"]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        log("timing the CPU baseline (oracle port + scipy) ...")
+        cpu = cpu_baseline(args.ref_n0)
+
+    cells_total = fp.n_cell * world
+    out = {
+        "metric": METRIC, "value": cells_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "syn-1M patch-family overlay (2 meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
+                   "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
+                   "nnz": info["nnz"], "rtol_true_residual": args.rtol,
+                   "l2": "inputs larger than L2 (CSR 0.45 GB, block values 1.6 GB vs 126 MB L2)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one problem per GPU)"},
+        "e2e": {"value": cells_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+        "assembly_cells_per_s": fp.n_cell * world / ((phases["symbolic_ms"] + phases["integrate_ms"] + phases["numeric_ms"]) / args.steps * 1e-3),
+        "pcg": {"iterations": si["iterations"], "converged": si["converged"], "relres_true": si["relres_true"],
+                "restarts": si["restarts"], "iterations_per_s": si["iterations"] / (phases["solve_ms"] / args.steps * 1e-3)},
+        "kernels": kernels,
+        "energy": last["energy"],
+        "prep_s": prep_s,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,9 @@ extern "C" {
 typedef struct mofem_ctx mofem_ctx;
 
 /* Flattened problem (SoA).  Pointers may be HOST or DEVICE pointers (detected
- * with cudaPointerGetAttributes); the context copies what it needs.
+ * with cudaPointerGetAttributes).  Host arrays are copied to the device inside
+ * mofem_set_problem; device arrays are BORROWED (zero-copy) and must stay alive
+ * and unchanged until the next mofem_set_problem / mofem_destroy.
  * Cell order is the reference's emission order: regular elements first, then
  * overlay cells in `polygons` order. */
 typedef struct {
@@ -134,6 +136,12 @@ int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double 
  * [0] symbolic, [1] integrate kernels, [2] numeric reduce, [3] solve, [4] h2d, [5] d2h.
  * counts: launches[0..3] = kernel launches in symbolic / integrate / numeric / solve. */
 int mofem_get_timing(mofem_ctx *ctx, double ms[6], int64_t launches[4]);
+
+/* Per-kernel profile of the PCG loop: when on, every iteration of mofem_solve records CUDA events around its three
+ * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
+ * kernels of the last mofem_solve, *iterations = iterations profiled. */
+int mofem_set_profile(mofem_ctx *ctx, int on);
+int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,8 @@ class MofemSolveInfo(C.Structure):
 # every symbol include/mofem_b200.h declares (tests check the library exports all of them)
 EXPORTS = ("mofem_create", "mofem_destroy", "mofem_last_error", "mofem_version", "mofem_stream", "mofem_set_problem",
            "mofem_symbolic", "mofem_assemble", "mofem_get_info", "mofem_get_csr", "mofem_get_coo_values",
-           "mofem_set_system", "mofem_solve", "mofem_energy", "mofem_spmv", "mofem_assemble_solve", "mofem_get_timing")
+           "mofem_set_system", "mofem_solve", "mofem_energy", "mofem_spmv", "mofem_assemble_solve", "mofem_get_timing", "mofem_set_profile",
+           "mofem_get_pcg_profile")
 
 _lib = None
 
@@ -74,6 +75,8 @@ def load():
                                        C.POINTER(MofemSolveInfo)]
     L.mofem_assemble_solve.restype = C.c_int
     L.mofem_get_timing.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_timing.restype = C.c_int
+    L.mofem_set_profile.argtypes = [vp, C.c_int]; L.mofem_set_profile.restype = C.c_int
+    L.mofem_get_pcg_profile.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_pcg_profile.restype = C.c_int
     _lib = L
     return L
 

@@ -37,7 +37,12 @@ struct mofem_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms[6]{};
     int64_t launches[4]{};
+    // optional per-kernel profile of the PCG loop
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    double prof_ms[4]{};
 };
+constexpr int PCG_CHUNK = 50;
 
 static int ctx_fail(mofem_ctx *ctx, int code, const std::string &msg)
 {
@@ -81,6 +86,7 @@ static int upload(mofem_ctx *ctx, const T *src, int64_t count, const T **out, st
 {
     *out = nullptr;
     if (!src) return MOFEM_OK;
+    if (is_device_ptr(src)) { *out = src; return MOFEM_OK; }  // device-resident input: borrowed, zero-copy
     T *d = nullptr;
     int rc = dev_alloc(ctx, &d, count, pool);
     if (rc) return rc;
@@ -133,6 +139,7 @@ void mofem_destroy(mofem_ctx *ctx)
     free_pool(ctx->problem_allocs); free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
     cudaFree(ctx->stats); cudaFree(ctx->err_flag);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -444,7 +451,17 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
     mofem_solve_info_t local;
     if (!info) info = &local;
     tic(ctx);
-    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, rtol, maxit, 50, info, s, &ctx->launches[3]));
+    cudaEvent_t *prof = nullptr;
+    if (ctx->profile) {
+        while ((int)ctx->prof_events.size() < 4 * PCG_CHUNK) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            ctx->prof_events.push_back(ev);
+        }
+        prof = ctx->prof_events.data();
+        for (double &v : ctx->prof_ms) v = 0.0;
+    }
+    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, rtol, maxit, PCG_CHUNK, info, s, &ctx->launches[3], prof, ctx->prof_ms));
     CK(pcg_finish(n, ctx->W, ctx->u, s));
     ctx->launches[3]++;
     ctx->ms[3] = toc(ctx);
@@ -502,6 +519,21 @@ int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double 
     if ((rc = mofem_set_system(ctx, rhs, fixed, fixed_value))) return rc;
     if ((rc = mofem_solve(ctx, rtol, maxit, u, info))) return rc;
     if (energy && (rc = mofem_energy(ctx, energy))) return rc;
+    return MOFEM_OK;
+}
+
+int mofem_set_profile(mofem_ctx *ctx, int on)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    ctx->profile = on != 0;
+    return MOFEM_OK;
+}
+
+int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    if (ms) for (int i = 0; i < 3; i++) ms[i] = ctx->prof_ms[i];
+    if (iterations) *iterations = (int64_t)ctx->prof_ms[3];
     return MOFEM_OK;
 }
 

@@ -109,7 +109,7 @@ struct PcgBuffers {
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
                       PcgBuffers &w, cudaStream_t s, int64_t *launches);
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, double rtol, int maxit, int chunk,
-                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches);
+                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms);
 cudaError_t pcg_finish(int64_t n, PcgBuffers &w, double *u_dev, cudaStream_t s);
 cudaError_t energy_of(const DevSystem &A, const double *u, double *q_tmp, double *part, double *out_dev, cudaStream_t s);
 

@@ -262,8 +262,10 @@ cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed,
 }
 
 // Runs PCG; returns via info.  `chunk` iterations are enqueued between host residual checks.
+// prof (optional): 4*chunk events; prof_ms[0..2] accumulate the device time of the SpMV / update / direction kernels,
+// prof_ms[3] the number of profiled iterations.
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, double rtol, int maxit, int chunk,
-                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches)
+                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
     const int64_t n = A.n, n_node = n / 2;
     const int gv = vec_grid(n), gs = spmv_grid(n_node);
@@ -289,15 +291,28 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, dou
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
         for (int k = 0; k < todo; k++, it++) {
+            if (prof) cudaEventRecord(prof[4 * k], s);
             k_spmv<<<gs, VEC_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c);
+            if (prof) cudaEventRecord(prof[4 * k + 1], s);
             k_pcg_update<<<gv, VEC_BLOCK, 0, s>>>(n, it, w.part_c, gs, w.sc, w.p, w.q, w.dinv, w.x, w.r, w.part_a, w.part_b);
+            if (prof) cudaEventRecord(prof[4 * k + 2], s);
             k_pcg_direction<<<gv, VEC_BLOCK, 0, s>>>(n, it, w.part_a, w.part_b, gv, w.sc, w.r, w.dinv, w.p, nullptr);
+            if (prof) cudaEventRecord(prof[4 * k + 3], s);
         }
         if (launches) *launches += 3 * (int64_t)todo;
         e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 4, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return e;
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return e;
+        if (prof) {
+            for (int k = 0; k < todo; k++)
+                for (int j = 0; j < 3; j++) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, prof[4 * k + j], prof[4 * k + j + 1]);
+                    prof_ms[j] += ms;
+                }
+            prof_ms[3] += todo;
+        }
         info->iterations = it;
         info->relres_rec = sqrt(sc_host[2] / bnorm2);
         if (!(sc_host[2] == sc_host[2])) break;  // NaN: breakdown

@@ -170,6 +170,17 @@ class Context:
         return u, e.value, dict(iterations=si.iterations, converged=int(si.converged), relres_true=si.relres_true,
                                 relres_rec=si.relres_rec, restarts=si.restarts)
 
+    def set_profile(self, on=True):
+        self._ck(self._L.mofem_set_profile(self._h, int(bool(on))))
+        return self
+
+    def pcg_profile(self) -> dict:
+        """Summed device time (ms) of the three PCG kernels over the last solve (needs ``set_profile(True)``)."""
+        ms = (C.c_double * 3)()
+        it = C.c_int64(0)
+        self._ck(self._L.mofem_get_pcg_profile(self._h, ms, C.byref(it)))
+        return dict(spmv_ms=ms[0], update_ms=ms[1], direction_ms=ms[2], iterations=int(it.value))
+
     def timing(self) -> dict:
         ms = (C.c_double * 6)()
         ln = (C.c_int64 * 4)()
