@@ -65,19 +65,21 @@ static int dev_alloc(mofem_ctx *ctx, T **out, int64_t count, std::vector<void *>
     *out = nullptr;
     if (count <= 0) count = 1;
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, sizeof(T) * (size_t)count);
+    // stream-ordered allocation from the device's default pool (release threshold raised in mofem_create): after
+    // the first pass over a problem size every allocation of the symbolic / solve phases is a pool hit
+    cudaError_t e = cudaMallocAsync(&p, sizeof(T) * (size_t)count, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return ctx_fail(ctx, MOFEM_E_NOMEM, std::string("cudaMalloc of ") + std::to_string(sizeof(T) * (size_t)count) + " bytes: " + cudaGetErrorString(e));
+        return ctx_fail(ctx, MOFEM_E_NOMEM, std::string("cudaMallocAsync of ") + std::to_string(sizeof(T) * (size_t)count) + " bytes: " + cudaGetErrorString(e));
     }
     pool.push_back(p);
     *out = (T *)p;
     return MOFEM_OK;
 }
 
-static void free_pool(std::vector<void *> &pool)
+static void free_pool(mofem_ctx *ctx, std::vector<void *> &pool)
 {
-    for (void *p : pool) cudaFree(p);
+    for (void *p : pool) cudaFreeAsync(p, ctx->stream);
     pool.clear();
 }
 
@@ -127,6 +129,11 @@ int mofem_create(mofem_ctx **out, int device)
     }
     cudaMalloc(&ctx->stats, sizeof(unsigned long long) * 4);
     cudaMalloc(&ctx->err_flag, sizeof(int));
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;  // keep freed blocks cached in the pool instead of returning them to the driver
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     *out = ctx;
     return MOFEM_OK;
 }
@@ -136,7 +143,8 @@ void mofem_destroy(mofem_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_pool(ctx->problem_allocs); free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    free_pool(ctx, ctx->problem_allocs); free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
+    cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->stats); cudaFree(ctx->err_flag);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
@@ -160,7 +168,7 @@ int mofem_set_problem(mofem_ctx *ctx, const mofem_problem_t *p)
         return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_problem: null array");
     if ((p->tri_curved != nullptr) != (p->tri_mid != nullptr))
         return ctx_fail(ctx, MOFEM_E_ARG, "tri_curved and tri_mid must be given together");
-    free_pool(ctx->problem_allocs); free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    free_pool(ctx, ctx->problem_allocs); free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
     ctx->have_problem = ctx->have_symbolic = ctx->have_matrix = ctx->have_system = ctx->have_solution = false;
     tic(ctx);
     DevProblem &P = ctx->P;
@@ -190,7 +198,7 @@ int mofem_symbolic(mofem_ctx *ctx)
 {
     if (!ctx || !ctx->have_problem) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_symbolic: call mofem_set_problem first");
     CK(cudaSetDevice(ctx->device));
-    free_pool(ctx->sym_allocs); free_pool(ctx->sys_allocs);
+    free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
     ctx->have_symbolic = ctx->have_matrix = ctx->have_system = ctx->have_solution = false;
     cudaStream_t s = ctx->stream;
     const DevProblem &P = ctx->P;
@@ -203,7 +211,7 @@ int mofem_symbolic(mofem_ctx *ctx)
     int32_t *ntask, *npair, *ncoo;
     int64_t *task_off, *pair_off, *coo_off;
     std::vector<void *> tmp;
-    auto cleanup = [&]() { free_pool(tmp); };
+    auto cleanup = [&]() { free_pool(ctx, tmp); };
     if ((rc = dev_alloc(ctx, &ntask, P.n_cell, tmp)) || (rc = dev_alloc(ctx, &npair, P.n_cell, tmp)) ||
         (rc = dev_alloc(ctx, &ncoo, P.n_cell, tmp)) || (rc = dev_alloc(ctx, &task_off, P.n_cell + 1, tmp)) ||
         (rc = dev_alloc(ctx, &pair_off, P.n_cell + 1, tmp)) || (rc = dev_alloc(ctx, &coo_off, P.n_cell + 1, tmp))) {
@@ -341,16 +349,16 @@ int mofem_get_csr(mofem_ctx *ctx, int32_t *indptr, int32_t *indices, double *dat
     int rc = MOFEM_OK;
     int32_t *ip = nullptr, *ix = nullptr;
     if (indptr) { if (is_device_ptr(indptr)) ip = indptr; else if ((rc = dev_alloc(ctx, &ip, nrow + 1, tmp))) return rc; }
-    if (indices) { if (is_device_ptr(indices)) ix = indices; else if ((rc = dev_alloc(ctx, &ix, nnz, tmp))) { free_pool(tmp); return rc; } }
+    if (indices) { if (is_device_ptr(indices)) ix = indices; else if ((rc = dev_alloc(ctx, &ix, nnz, tmp))) { free_pool(ctx, tmp); return rc; } }
     cudaError_t e = csr_export_pattern(ctx->C, ip, ix, s);
     if (e == cudaSuccess && indptr && ip != indptr) e = cudaMemcpyAsync(indptr, ip, sizeof(int32_t) * (nrow + 1), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && indices && ix != indices) e = cudaMemcpyAsync(indices, ix, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && data) {
-        if (!ctx->have_matrix) { free_pool(tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_csr: values requested before mofem_assemble"); }
+        if (!ctx->have_matrix) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_get_csr: values requested before mofem_assemble"); }
         e = cudaMemcpyAsync(data, ctx->data, sizeof(double) * nnz, cudaMemcpyDefault, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    free_pool(tmp);
+    free_pool(ctx, tmp);
     if (e != cudaSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("mofem_get_csr: ") + cudaGetErrorString(e));
     return MOFEM_OK;
 }
@@ -414,7 +422,7 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
     const int64_t n = 2 * ctx->P.n_node;
     int rc;
     if (ctx->sys_n != n || ctx->sys_allocs.empty()) {
-        free_pool(ctx->sys_allocs);
+        free_pool(ctx, ctx->sys_allocs);
         auto &pool = ctx->sys_allocs;
         PcgBuffers &W = ctx->W;
         if ((rc = dev_alloc(ctx, &W.x, n, pool)) || (rc = dev_alloc(ctx, &W.r, n, pool)) || (rc = dev_alloc(ctx, &W.p, n, pool)) ||
@@ -499,11 +507,11 @@ int mofem_spmv(mofem_ctx *ctx, const double *x, double *y)
     const double *xd = x; double *yd = y;
     int rc;
     if (!is_device_ptr(x)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) return rc; CK(cudaMemcpyAsync(t, x, sizeof(double) * n, cudaMemcpyHostToDevice, s)); xd = t; }
-    if (!is_device_ptr(y)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) { free_pool(tmp); return rc; } yd = t; }
+    if (!is_device_ptr(y)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) { free_pool(ctx, tmp); return rc; } yd = t; }
     cudaError_t e = spmv(system_of(ctx), xd, yd, nullptr, s);
     if (e == cudaSuccess && yd != y) e = cudaMemcpyAsync(y, yd, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    free_pool(tmp);
+    free_pool(ctx, tmp);
     if (e != cudaSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("mofem_spmv: ") + cudaGetErrorString(e));
     return MOFEM_OK;
 }
