@@ -137,6 +137,20 @@ int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double 
  * counts: launches[0..3] = kernel launches in symbolic / integrate / numeric / solve. */
 int mofem_get_timing(mofem_ctx *ctx, double ms[6], int64_t launches[4]);
 
+/* row-partitioned solve, one process per GPU ------------------------------------------------------------
+ * Each rank holds a LOCAL problem (mofem_b200/partition.py): every cell that touches a node it owns, nodes
+ * renumbered [owned | ghosts grouped by owner rank].  Assembly needs no exchange (rows of owned nodes are
+ * complete); the PCG exchanges the ghost entries of the search direction once per iteration (ncclSend/Recv)
+ * and all-reduces the dot products (NCCL over NVLink).  mofem_solve / mofem_energy / mofem_spmv then act on the
+ * owned rows; vectors passed in and out are LOCAL (owned + ghost entries). */
+int mofem_dist_unique_id(uint8_t id[128]);                 /* rank 0: ncclGetUniqueId, to be broadcast by the caller */
+int mofem_dist_init(mofem_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
+/* send_ptr/recv_ptr: [n_neighbor+1] in nodes; send_idx: local ids of owned nodes to send, neighbour by neighbour;
+ * the ghosts received from neighbour k are local nodes n_owned_node + recv_ptr[k] .. + recv_ptr[k+1]. */
+int mofem_set_halo(mofem_ctx *ctx, int64_t n_owned_node, int32_t n_neighbor, const int32_t *neighbor_rank,
+                   const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr);
+int mofem_clear_halo(mofem_ctx *ctx);
+
 /* Per-kernel profile of the PCG loop: when on, every iteration of mofem_solve records CUDA events around its three
  * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */

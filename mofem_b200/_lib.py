@@ -41,7 +41,7 @@ class MofemSolveInfo(C.Structure):
 EXPORTS = ("mofem_create", "mofem_destroy", "mofem_last_error", "mofem_version", "mofem_stream", "mofem_set_problem",
            "mofem_symbolic", "mofem_assemble", "mofem_get_info", "mofem_get_csr", "mofem_get_coo_values",
            "mofem_set_system", "mofem_solve", "mofem_energy", "mofem_spmv", "mofem_assemble_solve", "mofem_get_timing", "mofem_set_profile",
-           "mofem_get_pcg_profile")
+           "mofem_get_pcg_profile", "mofem_dist_unique_id", "mofem_dist_init", "mofem_set_halo", "mofem_clear_halo")
 
 _lib = None
 
@@ -75,6 +75,10 @@ def load():
                                        C.POINTER(MofemSolveInfo)]
     L.mofem_assemble_solve.restype = C.c_int
     L.mofem_get_timing.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_timing.restype = C.c_int
+    L.mofem_dist_unique_id.argtypes = [vp]; L.mofem_dist_unique_id.restype = C.c_int
+    L.mofem_dist_init.argtypes = [vp, vp, C.c_int32, C.c_int32]; L.mofem_dist_init.restype = C.c_int
+    L.mofem_set_halo.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp]; L.mofem_set_halo.restype = C.c_int
+    L.mofem_clear_halo.argtypes = [vp]; L.mofem_clear_halo.restype = C.c_int
     L.mofem_set_profile.argtypes = [vp, C.c_int]; L.mofem_set_profile.restype = C.c_int
     L.mofem_get_pcg_profile.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_pcg_profile.restype = C.c_int
     _lib = L

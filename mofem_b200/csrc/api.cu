@@ -38,6 +38,10 @@ struct mofem_ctx {
     double ms[6]{};
     int64_t launches[4]{};
     // optional per-kernel profile of the PCG loop
+    // row-partitioned solve (one process per GPU)
+    DistPlan dist;
+    bool have_halo = false;
+    std::vector<void *> dist_allocs;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     double prof_ms[4]{};
@@ -144,7 +148,9 @@ void mofem_destroy(mofem_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_pool(ctx, ctx->problem_allocs); free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
+    free_pool(ctx, ctx->dist_allocs);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->dist.comm) ncclCommDestroy(ctx->dist.comm);
     cudaFree(ctx->stats); cudaFree(ctx->err_flag);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
@@ -410,8 +416,10 @@ static DevSystem system_of(mofem_ctx *ctx)
 {
     DevSystem A;
     A.n = 2 * ctx->P.n_node; A.node_ptr = ctx->C.node_ptr; A.node_idx = ctx->C.node_idx; A.data = ctx->data;
+    A.n_own = ctx->have_halo ? 2 * ctx->dist.n_owned_node : A.n;
     return A;
 }
+static const DistPlan *dist_of(mofem_ctx *ctx) { return ctx->have_halo ? &ctx->dist : nullptr; }
 
 int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, const double *fixed_value)
 {
@@ -429,11 +437,10 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
             (rc = dev_alloc(ctx, &W.q, n, pool)) || (rc = dev_alloc(ctx, &W.dinv, n, pool)) || (rc = dev_alloc(ctx, &W.b, n, pool)) ||
             (rc = dev_alloc(ctx, &W.ufix, n, pool)) || (rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
-            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &W.counters, 4, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;
-        W.rr_hist = nullptr;
         ctx->sys_n = n;
     }
     tic(ctx);
@@ -442,7 +449,8 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
     CK(cudaMemcpyAsync(ctx->fixed_val, fixed_value, sizeof(double) * n, cudaMemcpyDefault, s));
     ctx->ms[4] += toc(ctx);
     ctx->launches[3] = 0;
-    CK(pcg_setup(system_of(ctx), ctx->rhs, ctx->fixed, ctx->fixed_val, ctx->W, s, &ctx->launches[3]));
+    if (ctx->have_halo && ctx->dist.n_owned_node > ctx->P.n_node) return ctx_fail(ctx, MOFEM_E_ARG, "halo plan does not match the problem");
+    CK(pcg_setup(system_of(ctx), ctx->rhs, ctx->fixed, ctx->fixed_val, ctx->W, dist_of(ctx), s, &ctx->launches[3]));
     CK(cudaStreamSynchronize(s));
     ctx->have_system = true;
     ctx->have_solution = false;
@@ -461,7 +469,7 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
     tic(ctx);
     cudaEvent_t *prof = nullptr;
     if (ctx->profile) {
-        while ((int)ctx->prof_events.size() < 4 * PCG_CHUNK) {
+        while ((int)ctx->prof_events.size() < 2 * 4 * PCG_CHUNK) {
             cudaEvent_t ev;
             CK(cudaEventCreate(&ev));
             ctx->prof_events.push_back(ev);
@@ -469,8 +477,8 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
         prof = ctx->prof_events.data();
         for (double &v : ctx->prof_ms) v = 0.0;
     }
-    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, rtol, maxit, PCG_CHUNK, info, s, &ctx->launches[3], prof, ctx->prof_ms));
-    CK(pcg_finish(n, ctx->W, ctx->u, s));
+    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s, &ctx->launches[3], prof, ctx->prof_ms));
+    CK(pcg_finish(system_of(ctx), ctx->W, dist_of(ctx), ctx->u, s));
     ctx->launches[3]++;
     ctx->ms[3] = toc(ctx);
     ctx->have_solution = true;
@@ -489,9 +497,9 @@ int mofem_energy(mofem_ctx *ctx, double *energy)
     if (!ctx || !ctx->have_solution || !energy) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_energy: call mofem_solve first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    CK(energy_of(system_of(ctx), ctx->u, ctx->W.q, ctx->W.part_c, ctx->W.sc + 5, s));
+    CK(energy_of(system_of(ctx), ctx->u, ctx->W, dist_of(ctx), ctx->W.sc + 6, s));
     double e = 0;
-    CK(cudaMemcpyAsync(&e, ctx->W.sc + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&e, ctx->W.sc + 6, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *energy = 0.5 * e;
     return MOFEM_OK;
@@ -527,6 +535,64 @@ int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double 
     if ((rc = mofem_set_system(ctx, rhs, fixed, fixed_value))) return rc;
     if ((rc = mofem_solve(ctx, rtol, maxit, u, info))) return rc;
     if (energy && (rc = mofem_energy(ctx, energy))) return rc;
+    return MOFEM_OK;
+}
+
+// ---- row-partitioned solve -------------------------------------------------------------------------------------
+int mofem_dist_unique_id(uint8_t id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return MOFEM_E_CUDA;
+    memcpy(id, &u, 128);
+    return MOFEM_OK;
+}
+
+int mofem_dist_init(mofem_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world)
+{
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_dist_init: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->dist.comm) { ncclCommDestroy(ctx->dist.comm); ctx->dist.comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclResult_t r = ncclCommInitRank(&ctx->dist.comm, world, u, rank);
+    if (r != ncclSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    ctx->dist.world = world; ctx->dist.rank = rank;
+    return MOFEM_OK;
+}
+
+int mofem_set_halo(mofem_ctx *ctx, int64_t n_owned_node, int32_t n_neighbor, const int32_t *neighbor_rank,
+                   const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    free_pool(ctx, ctx->dist_allocs);
+    ctx->have_halo = false;
+    ctx->have_system = ctx->have_solution = false;
+    if (n_neighbor < 0 || n_owned_node < 0) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_halo: negative size");
+    if (n_neighbor > 0 && (!neighbor_rank || !send_ptr || !recv_ptr)) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_halo: null array");
+    if (n_neighbor > 0 && !ctx->dist.comm) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_halo: call mofem_dist_init first");
+    DistPlan &D = ctx->dist;
+    D.n_owned_node = n_owned_node;
+    D.nb_rank.assign(neighbor_rank, neighbor_rank + n_neighbor);
+    D.send_ptr.assign(1, 0); D.recv_ptr.assign(1, 0);
+    if (n_neighbor) { D.send_ptr.assign(send_ptr, send_ptr + n_neighbor + 1); D.recv_ptr.assign(recv_ptr, recv_ptr + n_neighbor + 1); }
+    const int64_t n_send = D.send_ptr.back();
+    if (n_send && !send_idx) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_halo: null send_idx");
+    int rc;
+    if ((rc = dev_alloc(ctx, &D.send_idx, n_send, ctx->dist_allocs)) || (rc = dev_alloc(ctx, &D.sendbuf, 2 * n_send, ctx->dist_allocs))) return rc;
+    if (n_send) CK(cudaMemcpyAsync(D.send_idx, send_idx, sizeof(int32_t) * n_send, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_halo = true;
+    return MOFEM_OK;
+}
+
+int mofem_clear_halo(mofem_ctx *ctx)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    free_pool(ctx, ctx->dist_allocs);
+    ctx->have_halo = false;
+    ctx->have_system = ctx->have_solution = false;
     return MOFEM_OK;
 }
 

@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of the mofem_b200 CUDA library (internal).
 #pragma once
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -92,25 +93,38 @@ cudaError_t csr_export_pattern(const DevCsr &c, int32_t *indptr, int32_t *indice
 
 // pcg.cu
 struct DevSystem {
-    int64_t n;            // scalar unknowns (2 * n_node)
+    int64_t n;            // local scalar unknowns (2 * local nodes, ghosts included)
+    int64_t n_own;        // scalar rows this rank owns (== n on a single GPU); owned nodes come first
     const int64_t *node_ptr;
     const int32_t *node_idx;
     const double *data;   // scalar CSR values
 };
+
+// Row-partitioned operation: local node order is [owned | ghosts grouped by owner rank].
+struct DistPlan {
+    int world = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    int64_t n_owned_node = 0;
+    std::vector<int> nb_rank;                  // neighbour ranks
+    std::vector<int64_t> send_ptr, recv_ptr;   // [n_nb + 1], in nodes; recv offsets are relative to the ghost segment
+    int32_t *send_idx = nullptr;               // device: owned local node ids to send, neighbour by neighbour
+    double *sendbuf = nullptr;                 // device: 2 doubles per sent node
+};
+
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
 
-constexpr int PCG_MAX_PART = 2048;
+constexpr int PCG_MAX_PART = 4096;
 struct PcgBuffers {
     double *x, *r, *p, *q, *dinv, *b, *ufix;  // n each
     double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
     double *sc;                                // 8 scalars
-    double *rr_hist;                           // unused (reserved)
+    unsigned int *counters;                    // 4 arrival counters of the grid-wide reductions
 };
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
-                      PcgBuffers &w, cudaStream_t s, int64_t *launches);
-cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, double rtol, int maxit, int chunk,
-                    mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms);
-cudaError_t pcg_finish(int64_t n, PcgBuffers &w, double *u_dev, cudaStream_t s);
-cudaError_t energy_of(const DevSystem &A, const double *u, double *q_tmp, double *part, double *out_dev, cudaStream_t s);
+                      PcgBuffers &w, const DistPlan *dist, cudaStream_t s, int64_t *launches);
+cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist, double rtol, int maxit,
+                    int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms);
+cudaError_t pcg_finish(const DevSystem &A, PcgBuffers &w, const DistPlan *dist, double *u_dev, cudaStream_t s);
+cudaError_t energy_of(const DevSystem &A, const double *u, PcgBuffers &w, const DistPlan *dist, double *out_dev, cudaStream_t s);
 
 }  // namespace mofem

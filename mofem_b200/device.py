@@ -170,6 +170,29 @@ class Context:
         return u, e.value, dict(iterations=si.iterations, converged=int(si.converged), relres_true=si.relres_true,
                                 relres_rec=si.relres_rec, restarts=si.restarts)
 
+    # -- row-partitioned solve (one process per GPU) -------------------------------------------------
+    def dist_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._ck(self._L.mofem_dist_unique_id(buf))
+        return bytes(buf)
+
+    def dist_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._L.mofem_dist_init(self._h, buf, int(rank), int(world)))
+        return self
+
+    def set_halo(self, part):
+        """Install the halo plan of a :class:`mofem_b200.partition.LocalPart` (after ``exchange_send_lists``)."""
+        nb = _c(part.neighbors, np.int32)
+        sp = _c(part.send_ptr, np.int64); si = _c(part.send_idx, np.int32); rp = _c(part.recv_ptr, np.int64)
+        self._ck(self._L.mofem_set_halo(self._h, int(part.n_owned_node), int(len(nb)), _lib.ptr(nb), _lib.ptr(sp),
+                                        _lib.ptr(si) if len(si) else None, _lib.ptr(rp)))
+        return self
+
+    def clear_halo(self):
+        self._ck(self._L.mofem_clear_halo(self._h))
+        return self
+
     def set_profile(self, on=True):
         self._ck(self._L.mofem_set_profile(self._h, int(bool(on))))
         return self

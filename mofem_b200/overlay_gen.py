@@ -37,57 +37,64 @@ SEED = 20260101
 
 @dataclass
 class PatchMeshes:
-    n0: int
-    P: int                    # patches per direction
-    X0: np.ndarray            # [n0+1, n0+1, 2] mesh-0 node coordinates, indexed [j, i]
-    X1: np.ndarray            # [P, P, 6, 6, 2] mesh-1 node coordinates, indexed [b, a, t, s]
+    nx: int                   # mesh-0 elements per row (x); h = 1/nx
+    ny: int                   # mesh-0 element rows (y); the domain is [0,1] x [0,ny/nx]
+    Px: int                   # patches per direction
+    Py: int
+    X0: np.ndarray            # [ny+1, nx+1, 2] mesh-0 node coordinates, indexed [j, i]
+    X1: np.ndarray            # [Py, Px, 6, 6, 2] mesh-1 node coordinates, indexed [b, a, t, s]
 
     @property
-    def n_node0(self): return (self.n0 + 1) ** 2
+    def n0(self): return self.nx
     @property
-    def n_elem0(self): return self.n0 ** 2
+    def P(self): return self.Px
     @property
-    def n_node(self): return self.n_node0 + 36 * self.P ** 2
+    def n_node0(self): return (self.nx + 1) * (self.ny + 1)
     @property
-    def n_elem(self): return self.n_elem0 + 25 * self.P ** 2
+    def n_elem0(self): return self.nx * self.ny
+    @property
+    def n_node(self): return self.n_node0 + 36 * self.Px * self.Py
+    @property
+    def n_elem(self): return self.n_elem0 + 25 * self.Px * self.Py
 
     def node_xy(self):
         return np.concatenate([self.X0.reshape(-1, 2), self.X1.reshape(-1, 2)])
 
     def elem_nodes0(self):
-        n0 = self.n0
-        j, i = np.meshgrid(np.arange(n0), np.arange(n0), indexing="ij")
-        q = (j * (n0 + 1) + i).reshape(-1)
-        return np.stack([q, q + 1, q + n0 + 2, q + n0 + 1], 1)
+        nx, ny = self.nx, self.ny
+        j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+        q = (j * (nx + 1) + i).reshape(-1)
+        return np.stack([q, q + 1, q + nx + 2, q + nx + 1], 1)
 
     def elem_nodes1(self):
-        P = self.P
-        base = self.n_node0 + 36 * np.arange(P * P)
+        base = self.n_node0 + 36 * np.arange(self.Px * self.Py)
         t, s = np.meshgrid(np.arange(5), np.arange(5), indexing="ij")
         loc = (6 * t + s).reshape(-1)
         e = np.stack([loc, loc + 1, loc + 7, loc + 6], 1)             # [25, 4]
         return (base[:, None, None] + e[None]).reshape(-1, 4)
 
 
-def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED) -> PatchMeshes:
-    if n0 % PERIOD or n0 < PERIOD:
-        raise ValueError("n0 must be a positive multiple of 8")
-    h = 1.0 / n0
-    P = n0 // PERIOD
+def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED, ny: int = None) -> PatchMeshes:
+    nx = n0
+    ny = nx if ny is None else ny
+    if nx % PERIOD or nx < PERIOD or ny % PERIOD or ny < PERIOD:
+        raise ValueError("n0 (and ny) must be positive multiples of 8")
+    h = 1.0 / nx
+    Px, Py = nx // PERIOD, ny // PERIOD
     rng = np.random.default_rng(seed)
-    j, i = np.meshgrid(np.arange(n0 + 1), np.arange(n0 + 1), indexing="ij")
+    j, i = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
     X0 = np.stack([i, j], -1).astype(np.float64)
     jit0 = rng.uniform(-jitter, jitter, X0.shape)
     jit0[0, :] = jit0[-1, :] = 0.0
     jit0[:, 0] = jit0[:, -1] = 0.0
     X0 = (X0 + jit0) * h
-    b, a, t, s = np.meshgrid(np.arange(P), np.arange(P), np.arange(6), np.arange(6), indexing="ij")
+    b, a, t, s = np.meshgrid(np.arange(Py), np.arange(Px), np.arange(6), np.arange(6), indexing="ij")
     X1 = np.stack([PERIOD * a + OFF_X + s, PERIOD * b + OFF_Y + t], -1).astype(np.float64)
     jit1 = rng.uniform(-jitter, jitter, X1.shape)
     jit1[:, :, 0, :] = jit1[:, :, 5, :] = 0.0
     jit1[:, :, :, 0] = jit1[:, :, :, 5] = 0.0
     X1 = (X1 + jit1) * h
-    return PatchMeshes(n0=n0, P=P, X0=X0, X1=X1)
+    return PatchMeshes(nx=nx, ny=ny, Px=Px, Py=Py, X0=X0, X1=X1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -209,19 +216,28 @@ def _quad_triangles(poly):
 
 
 def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
-                 solver: int = SOLVER_LOWER, return_meshes: bool = False):
+                 solver: int = SOLVER_LOWER, return_meshes: bool = False, ny: int = None, patch_rows=None):
     """Flattened 2-mesh patch-family problem + its linear system.
 
     Returns ``(FlatProblem, rhs, fixed, fixed_value)``: left edge of mesh 0 clamped, concentrated load
-    ``(1, -0.5)`` at the bottom-right corner node of mesh 0."""
-    pm = patch_meshes(n0, jitter, seed)
-    P = pm.P
+    ``(1, -0.5)`` at the bottom-right corner node of mesh 0.
+
+    ``ny`` makes the domain a strip stack of ``ny`` element rows (weak scaling: one ``n0 x n0`` block per GPU).
+    ``patch_rows=(b_lo, b_hi)`` emits only the cells of the patch rows ``b_lo <= b < b_hi`` plus the mesh-0
+    element row directly below them (every cell that touches a node of that strip); node and element tables
+    stay global, so the result can go straight into :func:`mofem_b200.partition.partition_problem`."""
+    pm = patch_meshes(n0, jitter, seed, ny)
+    nx, ny = pm.nx, pm.ny
+    Px, Py = pm.Px, pm.Py
+    b_lo, b_hi = (0, Py) if patch_rows is None else (int(patch_rows[0]), int(patch_rows[1]))
+    if not (0 <= b_lo < b_hi <= Py):
+        raise ValueError("patch_rows out of range")
     X0, X1 = pm.X0, pm.X1
     n_elem0 = pm.n_elem0
-    node0 = lambda j, i: j * (n0 + 1) + i
-    elem0 = lambda j, i: j * n0 + i
+    node0 = lambda j, i: j * (nx + 1) + i
+    elem0 = lambda j, i: j * nx + i
 
-    b, a, q, p = np.meshgrid(np.arange(P), np.arange(P), np.arange(5), np.arange(5), indexing="ij")
+    b, a, q, p = np.meshgrid(np.arange(b_lo, b_hi), np.arange(Px), np.arange(5), np.arange(5), indexing="ij")
     C00 = X1[b, a, q, p]; C10 = X1[b, a, q, p + 1]; C11 = X1[b, a, q + 1, p + 1]; C01 = X1[b, a, q + 1, p]
     ip = PERIOD * a + 2 + p
     jp = PERIOD * b + 2 + q
@@ -231,10 +247,11 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     IS = _intersect(Pn, X0[jp - 1, ip], C00, C10)
     IN = _intersect(Pn, X0[jp + 1, ip], C01, C11)
     # straight patch borders: pin the border coordinate exactly
-    IW[:, :, :, 0, 0] = X1[:, :, 0:1, 0, 0]
-    IE[:, :, :, 4, 0] = X1[:, :, 0:1, 5, 0]
-    IS[:, :, 0, :, 1] = X1[:, :, 0, 0:1, 1]
-    IN[:, :, 4, :, 1] = X1[:, :, 5, 0:1, 1]
+    X1s = X1[b_lo:b_hi]
+    IW[:, :, :, 0, 0] = X1s[:, :, 0:1, 0, 0]
+    IE[:, :, :, 4, 0] = X1s[:, :, 0:1, 5, 0]
+    IS[:, :, 0, :, 1] = X1s[:, :, 0, 0:1, 1]
+    IN[:, :, 4, :, 1] = X1s[:, :, 5, 0:1, 1]
 
     # ---- two-element cells: 4 pieces per mesh-1 element ------------------------------------
     pieces = np.stack([
@@ -245,7 +262,7 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     ], 4)                                     # [P,P,5,5,4 pieces,4 verts,2]
     dxy = np.array([[0, 0], [1, 0], [1, 1], [0, 1]])
     e0_piece = elem0((jp - 1)[..., None] + dxy[:, 1], (ip - 1)[..., None] + dxy[:, 0])        # [P,P,5,5,4]
-    e1_piece = np.broadcast_to((n_elem0 + 25 * (b * P + a) + 5 * q + p)[..., None], e0_piece.shape)
+    e1_piece = np.broadcast_to((n_elem0 + 25 * (b * Px + a) + 5 * q + p)[..., None], e0_piece.shape)
     pieces = pieces.reshape(-1, 4, 2)
     e0_piece = e0_piece.reshape(-1); e1_piece = e1_piece.reshape(-1)
     n_piece = pieces.shape[0]
@@ -253,7 +270,7 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     en0 = pm.elem_nodes0(); en1 = pm.elem_nodes1()
     node_xy = pm.node_xy()
     w1 = np.zeros((6, 6)); w1[1:5, 1:5] = 1.0
-    node_w = np.concatenate([np.ones(pm.n_node0), np.tile(w1.reshape(-1), P * P)])
+    node_w = np.concatenate([np.ones(pm.n_node0), np.tile(w1.reshape(-1), Px * Py)])
 
     c0 = node_xy[en0[e0_piece]]                                   # [n_piece,4,2]
     c1 = node_xy[en1[e1_piece - n_elem0]]
@@ -274,10 +291,10 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     # ---- ring cells (one element, triangulated) -----------------------------------------------
     ring_elem, ring_tri_xy, ring_ptr = [], [], [0]
     X0l = X0.tolist()
-    for bb in range(P):
-        for aa in range(P):
-            iw = IW[bb, aa, :, 0].tolist(); ie = IE[bb, aa, :, 4].tolist()
-            is_ = IS[bb, aa, 0, :].tolist(); in_ = IN[bb, aa, 4, :].tolist()
+    for bb in range(b_lo, b_hi):
+        for aa in range(Px):
+            iw = IW[bb - b_lo, aa, :, 0].tolist(); ie = IE[bb - b_lo, aa, :, 4].tolist()
+            is_ = IS[bb - b_lo, aa, 0, :].tolist(); in_ = IN[bb - b_lo, aa, 4, :].tolist()
             m = X1[bb, aa].tolist()
             i1, j1 = PERIOD * aa + 1, PERIOD * bb + 1
             polys = []
@@ -314,11 +331,13 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     n_ring = len(ring_elem)
 
     # ---- untouched mesh-0 elements -> regular quadFE cells ------------------------------------------
-    touched = np.zeros((n0, n0), dtype=bool)
+    touched = np.zeros((ny, nx), dtype=bool)
     for d in range(6):
         for e in range(6):
-            touched[(PERIOD * np.arange(P) + 1 + d)[:, None], (PERIOD * np.arange(P) + 1 + e)[None, :]] = True
-    reg_elem = np.flatnonzero(~touched.reshape(-1))
+            touched[(PERIOD * np.arange(Py) + 1 + d)[:, None], (PERIOD * np.arange(Px) + 1 + e)[None, :]] = True
+    in_strip = np.zeros((ny, nx), dtype=bool)
+    in_strip[max(PERIOD * b_lo - 1, 0):PERIOD * b_hi, :] = True
+    reg_elem = np.flatnonzero((~touched & in_strip).reshape(-1))
     n_reg = len(reg_elem)
 
     # ---- assemble the SoA ----------------------------------------------------------------------------
@@ -344,17 +363,17 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     fp = FlatProblem(
         solver=int(solver), n_mesh=2, node_xy=np.ascontiguousarray(node_xy), elem_nodes=elem_nodes,
         elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
-        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.ones(25 * P * P, np.int32)]),
+        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.ones(25 * Px * Py, np.int32)]),
         mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), cell_elem=cell_elem, cell_kind=cell_kind,
         cell_tri_ptr=tri_ptr.astype(np.int64), tri_xy=np.ascontiguousarray(tri_xy),
         tri_rho=np.ascontiguousarray(tri_rho), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem])
 
     n_dof = 2 * pm.n_node
     fixed = np.zeros(n_dof, dtype=np.uint8)
-    left = node0(np.arange(n0 + 1), 0)
+    left = node0(np.arange(ny + 1), 0)
     fixed[2 * left] = 1; fixed[2 * left + 1] = 1
     rhs = np.zeros(n_dof)
-    rhs[2 * n0] = 1.0; rhs[2 * n0 + 1] = -0.5
+    rhs[2 * nx] = 1.0; rhs[2 * nx + 1] = -0.5
     out = (fp, rhs, fixed, np.zeros(n_dof))
     return out + (pm,) if return_meshes else out
 

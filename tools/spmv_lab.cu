@@ -190,22 +190,20 @@ int main(int argc, char **argv)
     run("rows lanes=" #L " block=" #B " minb=" #M " stream=" #S " unroll=" #UN " grid=" #G, [&]() {              \
         int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
         k_rows<L, B, M, S, UN><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
-    ROWS(8, 256, 1, false, 1, 8);
     ROWS(8, 256, 8, false, 1, 8);
-    ROWS(8, 256, 8, true, 1, 8);
-    ROWS(8, 256, 8, true, 1, 0);
-    ROWS(8, 256, 8, true, 2, 8);
-    ROWS(8, 256, 8, true, 2, 0);
-    ROWS(4, 256, 8, true, 1, 8);
-    ROWS(4, 256, 8, true, 2, 8);
-    ROWS(4, 256, 8, true, 2, 0);
-    ROWS(4, 256, 8, true, 4, 0);
-    ROWS(16, 256, 8, true, 1, 8);
-    ROWS(16, 256, 8, true, 2, 0);
-    ROWS(2, 256, 8, true, 4, 0);
     ROWS(8, 128, 16, true, 2, 0);
-    ROWS(8, 512, 4, true, 2, 0);
-    ROWS(32, 256, 8, true, 1, 0);
+    ROWS(8, 128, 16, false, 2, 0);
+    ROWS(8, 128, 16, true, 3, 0);
+    ROWS(8, 128, 16, true, 4, 0);
+    ROWS(8, 128, 12, true, 4, 0);
+    ROWS(8, 128, 8, true, 4, 0);
+    ROWS(8, 64, 32, true, 2, 0);
+    ROWS(8, 64, 32, true, 3, 0);
+    ROWS(16, 128, 16, true, 2, 0);
+    ROWS(8, 128, 16, true, 2, 16);
+    ROWS(8, 128, 16, true, 2, 32);
+    ROWS(8, 128, 16, true, 3, 16);
+    ROWS(8, 256, 8, true, 3, 0);
 
     // TMA-staged variant: tiles of <= TB blocks
     auto make_tiles = [&](int TB) {
@@ -229,12 +227,7 @@ int main(int argc, char **argv)
             k_tma<TBv, Bv, STv><<<148 * GM, Bv, sm>>>(nt, d_tr, d_ptr, d_idx, d_data, d_x, d_y); });             \
         cudaFree(d_tr);                                                                                          \
     }
-    TMA(512, 256, 3, 4);
-    TMA(1024, 256, 3, 2);
-    TMA(1024, 256, 2, 3);
-    TMA(1024, 512, 3, 2);
     TMA(2048, 512, 2, 1);
-    TMA(512, 128, 4, 4);
     // plain copy of the same number of bytes for reference
     {
         double *a, *b; size_t n = (size_t)(bytes / 16);
