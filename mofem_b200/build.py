@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lnccl"]
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

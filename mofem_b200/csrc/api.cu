@@ -150,7 +150,7 @@ void mofem_destroy(mofem_ctx *ctx)
     free_pool(ctx, ctx->problem_allocs); free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
     free_pool(ctx, ctx->dist_allocs);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->dist.comm) ncclCommDestroy(ctx->dist.comm);
+    if (ctx->dist.comm && nccl_api()) nccl_api()->CommDestroy(ctx->dist.comm);
     cudaFree(ctx->stats); cudaFree(ctx->err_flag);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
@@ -542,8 +542,10 @@ int mofem_assemble_solve(mofem_ctx *ctx, const mofem_problem_t *p, const double 
 int mofem_dist_unique_id(uint8_t id[128])
 {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    const NcclApi *nc = nccl_api();
+    if (!nc) return MOFEM_E_CUDA;
     ncclUniqueId u;
-    if (ncclGetUniqueId(&u) != ncclSuccess) return MOFEM_E_CUDA;
+    if (nc->GetUniqueId(&u) != ncclSuccess) return MOFEM_E_CUDA;
     memcpy(id, &u, 128);
     return MOFEM_OK;
 }
@@ -552,11 +554,13 @@ int mofem_dist_init(mofem_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t
 {
     if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_dist_init: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->dist.comm) { ncclCommDestroy(ctx->dist.comm); ctx->dist.comm = nullptr; }
+    const NcclApi *nc = nccl_api();
+    if (!nc) return ctx_fail(ctx, MOFEM_E_CUDA, "libnccl.so.2 could not be loaded");
+    if (ctx->dist.comm) { nc->CommDestroy(ctx->dist.comm); ctx->dist.comm = nullptr; }
     ncclUniqueId u;
     memcpy(&u, id, 128);
-    ncclResult_t r = ncclCommInitRank(&ctx->dist.comm, world, u, rank);
-    if (r != ncclSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    ncclResult_t r = nc->CommInitRank(&ctx->dist.comm, world, u, rank);
+    if (r != ncclSuccess) return ctx_fail(ctx, MOFEM_E_CUDA, std::string("ncclCommInitRank: ") + nc->GetErrorString(r));
     ctx->dist.world = world; ctx->dist.rank = rank;
     return MOFEM_OK;
 }

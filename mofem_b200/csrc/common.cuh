@@ -1,13 +1,13 @@
 // common.cuh -- shared declarations of the mofem_b200 CUDA library (internal).
 #pragma once
 #include <cuda_runtime.h>
-#include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
 #include <vector>
 
 #include "../../include/mofem_b200.h"
+#include "nccl_shim.h"
 
 namespace mofem {
 

@@ -301,20 +301,24 @@ static cudaError_t halo_exchange(const DistPlan *d, double *v, cudaStream_t s, i
                                                                       reinterpret_cast<double2 *>(d->sendbuf));
         if (launches) ++*launches;
     }
-    NCCL_OK(ncclGroupStart());
+    const NcclApi *nc = nccl_api();
+    if (!nc) return cudaErrorUnknown;
+    NCCL_OK(nc->GroupStart());
     for (size_t k = 0; k < d->nb_rank.size(); k++) {
         const int64_t ns = d->send_ptr[k + 1] - d->send_ptr[k], nr = d->recv_ptr[k + 1] - d->recv_ptr[k];
-        if (ns) NCCL_OK(ncclSend(d->sendbuf + 2 * d->send_ptr[k], (size_t)(2 * ns), ncclDouble, d->nb_rank[k], d->comm, s));
-        if (nr) NCCL_OK(ncclRecv(v + 2 * (d->n_owned_node + d->recv_ptr[k]), (size_t)(2 * nr), ncclDouble, d->nb_rank[k], d->comm, s));
+        if (ns) NCCL_OK(nc->Send(d->sendbuf + 2 * d->send_ptr[k], (size_t)(2 * ns), ncclDouble, d->nb_rank[k], d->comm, s));
+        if (nr) NCCL_OK(nc->Recv(v + 2 * (d->n_owned_node + d->recv_ptr[k]), (size_t)(2 * nr), ncclDouble, d->nb_rank[k], d->comm, s));
     }
-    NCCL_OK(ncclGroupEnd());
+    NCCL_OK(nc->GroupEnd());
     return cudaGetLastError();
 }
 
 static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStream_t s)
 {
     if (!d || d->world <= 1) return cudaSuccess;
-    NCCL_OK(ncclAllReduce(v, v, (size_t)count, ncclDouble, ncclSum, d->comm, s));
+    const NcclApi *nc = nccl_api();
+    if (!nc) return cudaErrorUnknown;
+    NCCL_OK(nc->AllReduce(v, v, (size_t)count, ncclDouble, ncclSum, d->comm, s));
     return cudaSuccess;
 }
 
