@@ -24,6 +24,7 @@ Fixtures written (npz, float64 / int32):
 """
 import copy
 import io
+import pickle
 import os
 import sys
 import contextlib
@@ -164,6 +165,50 @@ def pack(fp, I, J, V, extra=None):
     return d
 
 
+def dump_graph(input_data, overlapping_mesh, polygons, nep):
+    """The overlay object graph as plain builtins (tests/graph_fixture.py rebuilds duck-typed objects from it, so the
+    drop-in entry points can be called with the reference's own argument structure where /root/reference is absent)."""
+    pts, hes = {}, {}
+    P, H = [], []
+
+    def pid(p):
+        k = id(p)
+        if k not in pts:
+            pts[k] = len(P)
+            P.append([float(p.x), float(p.y), None if p.rho is None else [float(v) for v in p.rho]])
+        return pts[k]
+
+    def hid(h, follow=True):
+        k = id(h)
+        if k not in hes:
+            hes[k] = len(H)
+            H.append([pid(h.origin), pid(h.destination), -1, -1])
+        rec = H[hes[k]]
+        if follow and rec[2] == -1:
+            rec[2] = -2                      # being expanded
+            rec[2] = hid(h.next)
+            if getattr(h, "twin", None) is not None:
+                rec[3] = hid(h.twin, follow=False)
+        return hes[k]
+
+    face_id = {id(f): i for i, f in enumerate(polygons)}
+    elem_id = {id(e): [i, j] for i, mesh in enumerate(overlapping_mesh) if mesh is not None for j, e in enumerate(mesh)}
+    faces = []
+    for f in polygons:
+        inc = [None if e is None else elem_id[id(e)] for e in f.incidentElements]   # index into overlappingMesh
+        tris = None if f.triangles is None else [hid(t) for t in f.triangles]
+        faces.append([inc, tris])
+    elems = []
+    for mesh in overlapping_mesh:
+        if mesh is None:
+            elems.append(None)
+            continue
+        elems.append([[list(map(int, e.numbering)), [int(e.position[0]), int(e.position[1])],
+                       [face_id[id(f)] for f in e.polygons]] for e in mesh])
+    return {"points": P, "half_edges": H, "faces": faces, "elements": elems,
+            "node_elements_partial": [[list(t) for t in lst] for lst in nep], "input_data": input_data}
+
+
 def run_amore(stem, input_data=None):
     if input_data is None:
         input_data = inputF.txtInput(stem)
@@ -172,6 +217,7 @@ def run_amore(stem, input_data=None):
         overlapping_mesh, polygons, nep = overlay(input_data)
         fp = flatten(input_data, overlapping_mesh, polygons)
         constraints_in = copy.deepcopy(input_data[-3])
+        graph = dump_graph(copy.deepcopy(input_data), overlapping_mesh, polygons, nep)
         fn = {1: AMORE.lowerOrderAMORE, 2: AMORE.quadraticAMORE, 3: AMORE.quadraticICMAMORE}[solver]
         with Capture() as cap:
             out = fn(input_data, overlapping_mesh, polygons, nep)
@@ -185,7 +231,8 @@ def run_amore(stem, input_data=None):
     extra = dict(displacement=disp.reshape(-1), energy=np.array(energy).reshape(-1),
                  red_indptr=Kr.indptr.astype(np.int32), red_indices=Kr.indices.astype(np.int32), red_data=Kr.data,
                  red_rhs=fr.reshape(-1), red_x=xr.reshape(-1),
-                 constraints=np.array(constraints_in, dtype=np.float64))
+                 constraints=np.array(constraints_in, dtype=np.float64),
+                 graph=np.frombuffer(pickle.dumps(graph, protocol=4), dtype=np.uint8))
     print(stem, "cells", fp.n_cell, "tris", fp.n_tri, "coo", len(V), "energy", float(np.array(energy).reshape(-1)[0]))
     return pack(fp, I, J, V, extra), (input_data, overlapping_mesh, polygons, nep)
 
