@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--ref-n0", type=int, default=256, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events inside the PCG loop")
+    ap.add_argument("--l2-persist", type=int, default=1, help="pin the PCG vectors in L2 (library default: 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -263,6 +264,7 @@ def main():
     if world > 1:
         init_comm(ctx)
     ctx.set_profile(not args.no_profile)
+    ctx.set_option("l2_persist", args.l2_persist)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     maxit = 400000
     last = {}

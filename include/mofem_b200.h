@@ -155,6 +155,8 @@ int mofem_clear_halo(mofem_ctx *ctx);
  * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */
 int mofem_set_profile(mofem_ctx *ctx, int on);
+/* Tuning switches: "l2_persist" (default 1) pins the PCG vectors in L2 during mofem_solve. */
+int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value);
 int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ struct mofem_ctx {
     // tasks
     DevTasks T{};
     int32_t *cls_tasks = nullptr;
-    int64_t cls_count[N_CLASS]{}, cls_start[N_CLASS]{};
+    int64_t cls_count[N_BUCKET]{}, cls_start[N_BUCKET]{};
     int64_t n_pair = 0, n_coo = 0;
     std::vector<void *> sym_allocs;
     // csr
@@ -33,6 +33,9 @@ struct mofem_ctx {
     double *rhs = nullptr, *fixed_val = nullptr, *u = nullptr;
     std::vector<void *> sys_allocs;
     int64_t sys_n = 0;
+    double *slab = nullptr;
+    size_t slab_hot_bytes = 0;
+    int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms[6]{};
@@ -249,15 +252,15 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(launch_fill_tasks(P, task_off, pair_off, T, s)); L++;
     // class buckets
     int64_t *cls_count_d, *cls_start_d;
-    if ((rc = dev_alloc(ctx, &cls_count_d, N_CLASS, tmp)) || (rc = dev_alloc(ctx, &cls_start_d, N_CLASS, tmp))) { cleanup(); return rc; }
-    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_CLASS, s));
+    if ((rc = dev_alloc(ctx, &cls_count_d, N_BUCKET, tmp)) || (rc = dev_alloc(ctx, &cls_start_d, N_BUCKET, tmp))) { cleanup(); return rc; }
+    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_BUCKET, s));
     CKT(launch_bucket_tasks(T, cls_count_d, nullptr, nullptr, 0, s)); L++;
-    CKT(cudaMemcpyAsync(ctx->cls_count, cls_count_d, sizeof(int64_t) * N_CLASS, cudaMemcpyDeviceToHost, s));
+    CKT(cudaMemcpyAsync(ctx->cls_count, cls_count_d, sizeof(int64_t) * N_BUCKET, cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
     int64_t acc = 0;
-    for (int k = 0; k < N_CLASS; k++) { ctx->cls_start[k] = acc; acc += ctx->cls_count[k]; }
-    CKT(cudaMemcpyAsync(cls_start_d, ctx->cls_start, sizeof(int64_t) * N_CLASS, cudaMemcpyHostToDevice, s));
-    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_CLASS, s));
+    for (int k = 0; k < N_BUCKET; k++) { ctx->cls_start[k] = acc; acc += ctx->cls_count[k]; }
+    CKT(cudaMemcpyAsync(cls_start_d, ctx->cls_start, sizeof(int64_t) * N_BUCKET, cudaMemcpyHostToDevice, s));
+    CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_BUCKET, s));
     CKT(launch_bucket_tasks(T, cls_count_d, cls_start_d, ctx->cls_tasks, 1, s)); L++;
     // --- CSR symbolic ---------------------------------------------------------------------
     DevCsr &C = ctx->C;
@@ -312,8 +315,10 @@ int mofem_assemble(mofem_ctx *ctx)
     CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * 4, s));
     tic(ctx);
     for (int k = 0; k < N_CLASS; k++) {
-        if (!ctx->cls_count[k]) continue;
-        CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k], ctx->cls_count[k], ctx->blk_val,
+        int64_t n_cls = 0;
+        for (int b = 0; b < N_SUB; b++) n_cls += ctx->cls_count[k * N_SUB + b];
+        if (!n_cls) continue;
+        CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB], n_cls, ctx->blk_val,
                                   ctx->stats, s));
         ctx->launches[1]++;
     }
@@ -433,9 +438,14 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
         free_pool(ctx, ctx->sys_allocs);
         auto &pool = ctx->sys_allocs;
         PcgBuffers &W = ctx->W;
-        if ((rc = dev_alloc(ctx, &W.x, n, pool)) || (rc = dev_alloc(ctx, &W.r, n, pool)) || (rc = dev_alloc(ctx, &W.p, n, pool)) ||
-            (rc = dev_alloc(ctx, &W.q, n, pool)) || (rc = dev_alloc(ctx, &W.dinv, n, pool)) || (rc = dev_alloc(ctx, &W.b, n, pool)) ||
-            (rc = dev_alloc(ctx, &W.ufix, n, pool)) || (rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
+        // the five vectors the PCG loop touches every iteration live in one slab (the L2 persistence window of mofem_solve)
+        const int64_t npad = (n + 31) & ~(int64_t)31;
+        double *slab;
+        if ((rc = dev_alloc(ctx, &slab, 7 * npad, pool))) return rc;
+        W.p = slab; W.q = slab + npad; W.x = slab + 2 * npad; W.r = slab + 3 * npad; W.dinv = slab + 4 * npad;
+        W.b = slab + 5 * npad; W.ufix = slab + 6 * npad;
+        ctx->slab = slab; ctx->slab_hot_bytes = sizeof(double) * (size_t)(5 * npad);
+        if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &W.counters, 4, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
@@ -477,7 +487,34 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
         prof = ctx->prof_events.data();
         for (double &v : ctx->prof_ms) v = 0.0;
     }
-    CK(pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s, &ctx->launches[3], prof, ctx->prof_ms));
+    // L2 persistence: p, q, x, r, dinv (5 vectors) are re-read every iteration while 9 bytes per non-zero of matrix
+    // stream through the 126 MB L2 once; pin the vectors, let the matrix loads (evict-first) bypass them.
+    bool window = false;
+    if (ctx->l2_persist && ctx->slab_hot_bytes) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t want = std::min<size_t>(ctx->slab_hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = ctx->slab;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->slab_hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
+    cudaError_t run_err = pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s,
+                                  &ctx->launches[3], prof, ctx->prof_ms);
+    if (window) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
+    CK(run_err);
     CK(pcg_finish(system_of(ctx), ctx->W, dist_of(ctx), ctx->u, s));
     ctx->launches[3]++;
     ctx->ms[3] = toc(ctx);
@@ -605,6 +642,13 @@ int mofem_set_profile(mofem_ctx *ctx, int on)
     if (!ctx) return MOFEM_E_ARG;
     ctx->profile = on != 0;
     return MOFEM_OK;
+}
+
+int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return MOFEM_E_ARG;
+    if (!strcmp(name, "l2_persist")) { ctx->l2_persist = (int)value; return MOFEM_OK; }
+    return ctx_fail(ctx, MOFEM_E_ARG, std::string("mofem_set_option: unknown option ") + name);
 }
 
 int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations)

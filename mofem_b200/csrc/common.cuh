@@ -18,6 +18,10 @@ enum { CELL_REGULAR = 0, CELL_OVERLAY = 1 };
 //   0..4   regular element rules: tri3, quad4 (quadFE), quad4 (ICMFE), tri6, quad9
 //   8 + 2*(4*i1+i2) + curved   AMORE blocks, i = index of n in {3,4,6,9}
 constexpr int N_CLASS = 8 + 32;
+// tasks of one class are further grouped by (diagonal / off-diagonal, triangle count) so that the threads of a warp
+// run the same trip counts; a bucket id is class * N_SUB + sub
+constexpr int N_SUB = 16;
+constexpr int N_BUCKET = N_CLASS * N_SUB;
 __host__ __device__ inline int type_index(int nn) { return nn == 3 ? 0 : nn == 4 ? 1 : nn == 6 ? 2 : 3; }
 
 // device view of the flattened problem
@@ -39,7 +43,7 @@ struct DevTasks {
     int32_t *cell;      // [n_task]
     int32_t *e1, *e2;   // [n_task] global element ids (e2 == e1 for diagonal / regular)
     int32_t *slots;     // [n_task] mesh slot j | (l << 8)
-    int32_t *cls;       // [n_task] class id
+    int32_t *cls;       // [n_task] bucket id = class id * N_SUB + sub-bucket
     int64_t *pair_off;  // [n_task] offset of the block in blk_val, in node pairs (x4 doubles)
 };
 

@@ -164,6 +164,17 @@ __device__ __forceinline__ int task_class(const DevProblem &p, int64_t c, int n1
     return 8 + 2 * (4 * type_index(n1) + type_index(n2)) + curved;
 }
 
+__device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n1, int n2, bool regular, bool diag)
+{
+    const int cls = task_class(p, c, n1, n2, regular);
+    int sub = 0;
+    if (!regular) {
+        const int64_t nt = p.cell_tri_ptr[c + 1] - p.cell_tri_ptr[c];
+        sub = (diag ? 0 : 8) + (int)(nt < 7 ? nt : 7);
+    }
+    return cls * N_SUB + sub;
+}
+
 __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off, const int64_t *__restrict__ pair_off,
                              DevTasks t)
 {
@@ -177,7 +188,7 @@ __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off,
             if (ce[j] >= 0) {
                 int n = p.elem_nn[ce[j]];
                 t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[j]; t.slots[k] = j | (j << 8);
-                t.cls[k] = task_class(p, c, n, n, true); t.pair_off[k] = po;
+                t.cls[k] = task_bucket(p, c, n, n, true, true); t.pair_off[k] = po;
                 break;
             }
         return;
@@ -186,13 +197,13 @@ __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off,
         if (ce[j] < 0) continue;
         int n1 = p.elem_nn[ce[j]];
         t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[j]; t.slots[k] = j | (j << 8);
-        t.cls[k] = task_class(p, c, n1, n1, false); t.pair_off[k] = po;
+        t.cls[k] = task_bucket(p, c, n1, n1, false, true); t.pair_off[k] = po;
         k++; po += n1 * n1;
         for (int l = j + 1; l < M; l++) {
             if (ce[l] < 0) continue;
             int n2 = p.elem_nn[ce[l]];
             t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[l]; t.slots[k] = j | (l << 8);
-            t.cls[k] = task_class(p, c, n1, n2, false); t.pair_off[k] = po;
+            t.cls[k] = task_bucket(p, c, n1, n2, false, false); t.pair_off[k] = po;
             k++; po += n1 * n2;
         }
     }

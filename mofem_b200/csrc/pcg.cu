@@ -325,10 +325,10 @@ static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStrea
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
-static int vec_grid(int64_t n2)
+static int vec_grid(int64_t n2, int64_t cap = PCG_MAX_PART)
 {
     int64_t g = (n2 + VEC_BLOCK - 1) / VEC_BLOCK;
-    if (g > 148 * 8) g = 148 * 8;
+    if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
 }
@@ -396,7 +396,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
-    const int gv = vec_grid(n2), gs = spmv_grid(n_node);
+    const int gv = vec_grid(n2), gd = vec_grid(n2, 1 << 30), gs = spmv_grid(n_node);
     cudaError_t e;
     double sc_host[8];
     const double2 *b2 = reinterpret_cast<const double2 *>(w.b), *dinv2 = reinterpret_cast<const double2 *>(w.dinv);
@@ -452,7 +452,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
             k_pcg_update<<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b, w.counters + 1);
             if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
             if (ev) cudaEventRecord(ev[4 * k + 2], s);
-            k_pcg_direction<<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2);
+            k_pcg_direction<<<gd, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2);
             if (ev) cudaEventRecord(ev[4 * k + 3], s);
         }
         if (launches) *launches += 3 * (int64_t)todo;

@@ -193,6 +193,10 @@ class Context:
         self._ck(self._L.mofem_clear_halo(self._h))
         return self
 
+    def set_option(self, name: str, value: int):
+        self._ck(self._L.mofem_set_option(self._h, name.encode(), int(value)))
+        return self
+
     def set_profile(self, on=True):
         self._ck(self._L.mofem_set_profile(self._h, int(bool(on))))
         return self

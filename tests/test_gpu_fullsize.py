@@ -1,0 +1,94 @@
+"""Size-independent properties at the bench workload's full size (syn-1M: n0 = 664, 1.02 M overlay cells, 1.38 M DOF):
+where the oracle cannot finish in seconds, the CUDA path is checked through invariants of the discretisation, plus a
+random subsample of cells against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N0 = 664
+
+
+@pytest.fixture(scope="module")
+def big(gpu_ctx):
+    from mofem_b200 import overlay_gen
+    fp, rhs, fixed, val = overlay_gen.patch_family(N0)
+    gpu_ctx.clear_halo()
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    return fp, rhs, fixed, val
+
+
+def test_sizes_match_the_survey(big, gpu_ctx):
+    fp, *_ = big
+    info = gpu_ctx.info()
+    assert fp.n_dof == 2 * (665 ** 2 + 6889 * 36) == info["n_dof"]
+    # per patch period 28672 COO triplets, of which 28 untouched quadFE cells * 64
+    assert 0.99e6 < fp.n_cell < 1.03e6 and info["n_coo"] == 28672 * 6889 + 64 * (664 ** 2 - 64 * 6889)
+    assert info["nnz"] % 4 == 0 and 4.9e7 < info["nnz"] < 5.1e7
+
+
+def test_csr_structure(big, gpu_ctx):
+    indptr, indices, _ = gpu_ctx.csr(values=False)
+    assert indptr[0] == 0 and (np.diff(indptr) > 0).all()                    # every DOF has a row
+    row = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    key = row.astype(np.int64) * (len(indptr) - 1) + indices
+    assert (np.diff(key) > 0).all()                                          # sorted, no duplicates (canonical CSR)
+
+
+def test_symmetry_and_rigid_body_null_space(big, gpu_ctx):
+    fp, *_ = big
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(fp.n_dof), rng.standard_normal(fp.n_dof)
+    Kx, Ky = gpu_ctx.spmv(x), gpu_ctx.spmv(y)
+    assert abs(y @ Kx - x @ Ky) <= 1e-11 * abs(y @ Kx)                        # K = K^T
+    scale = np.abs(Kx).max()
+    tx = np.zeros(fp.n_dof); tx[0::2] = 1.0
+    ty = np.zeros(fp.n_dof); ty[1::2] = 1.0
+    rot = np.empty(fp.n_dof); rot[0::2] = -fp.node_xy[:, 1]; rot[1::2] = fp.node_xy[:, 0]
+    for mode in (tx, ty, rot):        # partition of unity + isoparametric completeness: K annihilates rigid motions
+        assert np.abs(gpu_ctx.spmv(mode)).max() <= 1e-9 * scale
+
+
+def test_linear_field_gives_constant_strain_energy(big, gpu_ctx):
+    # u = (a x, b y): E = 1/2 * area * eps^T D eps exactly (patch test at full size, domain = unit square)
+    fp, *_ = big
+    a, b = 1.7e-3, -0.4e-3
+    u = np.empty(fp.n_dof); u[0::2] = a * fp.node_xy[:, 0]; u[1::2] = b * fp.node_xy[:, 1]
+    D = fp.mat_D[0]
+    eps = np.array([a, b, 0.0])
+    exact = 0.5 * eps @ D @ eps
+    e = 0.5 * u @ gpu_ctx.spmv(u)
+    assert abs(e - exact) <= 1e-9 * exact
+
+
+def test_random_cell_subsample_against_the_oracle(big, gpu_ctx):
+    from mofem_b200.device import Context
+    from mofem_b200.flatten import FlatProblem
+    from oracle import oracle
+    fp, *_ = big
+    rng = np.random.default_rng(11)
+    cells = np.sort(rng.choice(fp.n_cell, 3000, replace=False))
+    tp = fp.cell_tri_ptr
+    cnt = tp[cells + 1] - tp[cells]
+    ptr = np.concatenate([[0], np.cumsum(cnt)])
+    sel = np.repeat(tp[cells] - ptr[:-1], cnt) + np.arange(ptr[-1])
+    sub = FlatProblem(solver=fp.solver, n_mesh=fp.n_mesh, node_xy=fp.node_xy, elem_nodes=fp.elem_nodes, elem_nn=fp.elem_nn,
+                      elem_mat=fp.elem_mat, elem_mesh=fp.elem_mesh, mat_D=fp.mat_D, cell_elem=fp.cell_elem[cells].copy(),
+                      cell_kind=fp.cell_kind[cells].copy(), cell_tri_ptr=ptr.astype(np.int64),
+                      tri_xy=fp.tri_xy[sel].copy(), tri_rho=fp.tri_rho[sel].copy())
+    I, J, V, _, newton = oracle.assemble_coo(sub, 4)
+    with Context(0) as ctx:
+        ctx.set_problem(sub).symbolic().assemble()
+        Vg = ctx.coo_values()
+        assert ctx.info()["newton_updates"] == newton
+    assert np.abs(Vg - V).max() <= 1e-12 * np.abs(V).max()
+
+
+def test_solve_energy_identity(big, gpu_ctx):
+    fp, rhs, fixed, val = big
+    gpu_ctx.set_system(rhs, fixed, val)
+    u, info = gpu_ctx.solve(rtol=1e-10)
+    assert info["converged"] == 1 and info["relres_true"] <= 1e-10
+    e = gpu_ctx.energy()
+    assert abs(e - 0.5 * rhs @ u) <= 1e-7 * e          # homogeneous Dirichlet data: 1/2 u^T K u = 1/2 f^T u at the solution
+    assert not u[fixed == 1].any()
