@@ -325,7 +325,7 @@ static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStrea
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
-static int vec_grid(int64_t n2, int64_t cap = PCG_MAX_PART)
+static int vec_grid(int64_t n2, int64_t cap = 148 * 8)
 {
     int64_t g = (n2 + VEC_BLOCK - 1) / VEC_BLOCK;
     if (g > cap) g = cap;
@@ -396,7 +396,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
-    const int gv = vec_grid(n2), gd = vec_grid(n2, 1 << 30), gs = spmv_grid(n_node);
+    const int gv = vec_grid(n2), gd = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
     double sc_host[8];
     const double2 *b2 = reinterpret_cast<const double2 *>(w.b), *dinv2 = reinterpret_cast<const double2 *>(w.dinv);
