@@ -216,16 +216,23 @@ def _quad_triangles(poly):
 
 
 def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
-                 solver: int = SOLVER_LOWER, return_meshes: bool = False, ny: int = None, patch_rows=None):
+                 solver: int = SOLVER_LOWER, return_meshes: bool = False, ny: int = None, patch_rows=None,
+                 n_mesh: int = 2):
     """Flattened 2-mesh patch-family problem + its linear system.
 
     Returns ``(FlatProblem, rhs, fixed, fixed_value)``: left edge of mesh 0 clamped, concentrated load
     ``(1, -0.5)`` at the bottom-right corner node of mesh 0.
 
+    ``n_mesh=3`` ("multi-mesh" config) distributes the patches over two overlapping meshes: patch ``(a, b)`` belongs to
+    mesh ``1 + (a+b) % 2``.  Cells then carry three mesh slots and three weight functions; the patches of meshes 1 and 2
+    do not overlap each other (three-element cells are covered by the simpleOFE3 / zoo fixtures instead).
+
     ``ny`` makes the domain a strip stack of ``ny`` element rows (weak scaling: one ``n0 x n0`` block per GPU).
     ``patch_rows=(b_lo, b_hi)`` emits only the cells of the patch rows ``b_lo <= b < b_hi`` plus the mesh-0
     element row directly below them (every cell that touches a node of that strip); node and element tables
     stay global, so the result can go straight into :func:`mofem_b200.partition.partition_problem`."""
+    if n_mesh not in (2, 3):
+        raise ValueError("n_mesh must be 2 or 3")
     pm = patch_meshes(n0, jitter, seed, ny)
     nx, ny = pm.nx, pm.ny
     Px, Py = pm.Px, pm.Py
@@ -275,18 +282,20 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     c0 = node_xy[en0[e0_piece]]                                   # [n_piece,4,2]
     c1 = node_xy[en1[e1_piece - n_elem0]]
     wgt1 = node_w[en1[e1_piece - n_elem0]]                        # [n_piece,4]
-    rho_piece = np.empty((n_piece, 4, 2))
+    patch_mesh = (1 + ((b + a) % 2 if n_mesh == 3 else 0 * b))            # [Py',Px,5,5] mesh of the patch
+    mesh_piece = np.broadcast_to(patch_mesh[..., None], (b_hi - b_lo, Px, 5, 5, 4)).reshape(-1)
+    rho_piece = np.zeros((n_piece, 4, n_mesh))
     for v in range(4):
         N0 = _inv_quad_N(c0, pieces[:, v])
         N1 = _inv_quad_N(c1, pieces[:, v])
         r0 = N0.sum(-1)                                           # weights of mesh 0 are all 1
         r1 = 9.0 * (N1 * wgt1).sum(-1)
         rho_piece[:, v, 0] = r0 / (r0 + r1)
-        rho_piece[:, v, 1] = r1 / (r0 + r1)
+        rho_piece[np.arange(n_piece), v, mesh_piece] = r1 / (r0 + r1)
     tri_idx = _quad_triangles(pieces)                             # [n_piece,2,3]
     ar = np.arange(n_piece)[:, None, None]
     piece_tri_xy = pieces[ar, tri_idx]                            # [n_piece,2,3,2]
-    piece_tri_rho = rho_piece[ar, tri_idx]                        # [n_piece,2,3,2]
+    piece_tri_rho = rho_piece[ar, tri_idx]                        # [n_piece,2,3,n_mesh]
 
     # ---- ring cells (one element, triangulated) -----------------------------------------------
     ring_elem, ring_tri_xy, ring_ptr = [], [], [0]
@@ -342,28 +351,28 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
 
     # ---- assemble the SoA ----------------------------------------------------------------------------
     C = n_reg + n_ring + n_piece
-    cell_elem = np.full((C, 2), -1, dtype=np.int32)
+    cell_elem = np.full((C, n_mesh), -1, dtype=np.int32)
     cell_kind = np.zeros(C, dtype=np.int32)
     cell_elem[:n_reg, 0] = reg_elem
     cell_elem[n_reg:n_reg + n_ring, 0] = ring_elem
     cell_kind[n_reg:] = CELL_OVERLAY
     cell_elem[n_reg + n_ring:, 0] = e0_piece
-    cell_elem[n_reg + n_ring:, 1] = e1_piece
+    cell_elem[n_reg + n_ring + np.arange(n_piece), mesh_piece] = e1_piece
     ntri = np.zeros(C, dtype=np.int64)
     ntri[n_reg:n_reg + n_ring] = np.diff(np.array(ring_ptr))
     ntri[n_reg + n_ring:] = 2
     tri_ptr = np.concatenate([[0], np.cumsum(ntri)])
-    ring_rho = np.zeros((len(ring_tri_xy), 3, 2)); ring_rho[:, :, 0] = 1.0
+    ring_rho = np.zeros((len(ring_tri_xy), 3, n_mesh)); ring_rho[:, :, 0] = 1.0
     tri_xy = np.concatenate([ring_tri_xy, piece_tri_xy.reshape(-1, 3, 2)])
-    tri_rho = np.concatenate([ring_rho, piece_tri_rho.reshape(-1, 3, 2)])
+    tri_rho = np.concatenate([ring_rho, piece_tri_rho.reshape(-1, 3, n_mesh)])
 
     elem_nodes = np.full((pm.n_elem, 9), -1, dtype=np.int32)
     elem_nodes[:n_elem0, :4] = en0
     elem_nodes[n_elem0:, :4] = en1
     fp = FlatProblem(
-        solver=int(solver), n_mesh=2, node_xy=np.ascontiguousarray(node_xy), elem_nodes=elem_nodes,
+        solver=int(solver), n_mesh=n_mesh, node_xy=np.ascontiguousarray(node_xy), elem_nodes=elem_nodes,
         elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
-        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.ones(25 * Px * Py, np.int32)]),
+        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.repeat(_patch_mesh_ids(Px, Py, n_mesh), 25)]),
         mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), cell_elem=cell_elem, cell_kind=cell_kind,
         cell_tri_ptr=tri_ptr.astype(np.int64), tri_xy=np.ascontiguousarray(tri_xy),
         tri_rho=np.ascontiguousarray(tri_rho), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem])
@@ -378,13 +387,22 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     return out + (pm,) if return_meshes else out
 
 
-def patch_deck(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3, solver: int = 1):
+def _patch_mesh_ids(Px, Py, n_mesh):
+    """Mesh id of every patch, patch-major order (b * Px + a)."""
+    b, a = np.meshgrid(np.arange(Py), np.arange(Px), indexing="ij")
+    return (1 + ((a + b) % 2 if n_mesh == 3 else 0 * a)).reshape(-1).astype(np.int32)
+
+
+def patch_deck(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3, solver: int = 1,
+               n_mesh: int = 2):
     """The same problem as a reference ``inputData`` tuple (inputFunctions/inputF.py:204-205, concentrated-force
     form), for pushing small sizes through the reference's own plane sweep."""
     pm = patch_meshes(n0, jitter, seed)
     coords = pm.node_xy().tolist()
-    meshes = [pm.elem_nodes0().tolist(), pm.elem_nodes1().tolist()]
-    material_mesh = [[0] * len(meshes[0]), [0] * len(meshes[1])]
+    en1 = pm.elem_nodes1()
+    ids = np.repeat(_patch_mesh_ids(pm.Px, pm.Py, n_mesh), 25)
+    meshes = [pm.elem_nodes0().tolist()] + [en1[ids == k].tolist() for k in range(1, n_mesh)]
+    material_mesh = [[0] * len(m) for m in meshes]
     constraints = [[j * (n0 + 1), 1, 1, 0.0, 0.0] for j in range(n0 + 1)]
     forces = [[], [[n0, 1.0, -0.5]]]
     return ([solver, 1], None, None, meshes, material_mesh, coords, [[E, nu]], constraints, [0, 0, 1], forces)

@@ -366,6 +366,8 @@ def main():
     planeSweepMeshes.scale = [1, 1]
     d, _ = run_amore("patch16", overlay_gen.patch_deck(16))
     np.savez_compressed(os.path.join(HERE, "patch16.npz"), **d)
+    d, _ = run_amore("patch16_m3", overlay_gen.patch_deck(16, n_mesh=3))     # three meshes (patches alternate)
+    np.savez_compressed(os.path.join(HERE, "patch16_m3.npz"), **d)
     for kind in ("lower", "icm", "quad"):
         np.savez_compressed(os.path.join(HERE, f"single_{kind}.npz"), **run_single(kind))
     for solver in (1, 2, 3):

@@ -13,9 +13,14 @@ def _canon_tris(t):
     return sorted(tuple(sorted(map(tuple, x))) for x in t)
 
 
-def test_generator_reproduces_the_reference_overlay():
-    fpr, d = load_golden("patch16")
-    fp, rhs, fixed, val = overlay_gen.patch_family(16)
+import pytest
+
+
+@pytest.mark.parametrize("name,n_mesh", [("patch16", 2), ("patch16_m3", 3)])
+def test_generator_reproduces_the_reference_overlay(name, n_mesh):
+    fpr, d = load_golden(name)
+    fp, rhs, fixed, val = overlay_gen.patch_family(16, n_mesh=n_mesh)
+    assert fp.n_mesh == fpr.n_mesh == n_mesh
     assert np.array_equal(fp.node_xy, fpr.node_xy)
     assert fp.n_cell == fpr.n_cell and fp.n_tri == fpr.n_tri
     assert _canon_tris(fp.tri_xy) == _canon_tris(fpr.tri_xy)          # same triangle set as the sweep + ear rule
