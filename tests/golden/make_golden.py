@@ -17,6 +17,7 @@ Fixtures written (npz, float64 / int32):
       single-mesh decks generated here.
   patch16.npz -- the synthetic patch family (n0=16, jittered) as a reference deck pushed through the
       reference's plane sweep + AMORE.lowerOrderAMORE: pins mofem_b200/overlay_gen.py.
+  shipped_solution_AMOREBracket.npz -- the numbers of the reference's shipped solution.txt (its only golden output).
   zoo_s{1,2,3}.npz -- array level: synthetic all-types problems pushed through
       stiffnessMatrix.{lowerOrderAMORE,quadraticAMORE,triFE,...} following the
       reference's cell loop.
@@ -368,6 +369,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "patch16.npz"), **d)
     d, _ = run_amore("patch16_m3", overlay_gen.patch_deck(16, n_mesh=3))     # three meshes (patches alternate)
     np.savez_compressed(os.path.join(HERE, "patch16_m3.npz"), **d)
+    # the reference's shipped golden output (solution.txt, AMOREBracket, solver 3) as numbers
+    from mofem_b200 import solution_io
+    disp, energy, name = solution_io.read_solution(os.path.join(REF, "solution.txt"))
+    np.savez_compressed(os.path.join(HERE, "shipped_solution_AMOREBracket.npz"), displacement=disp.reshape(-1),
+                        energy=energy.reshape(-1), name=np.array(name))
     for kind in ("lower", "icm", "quad"):
         np.savez_compressed(os.path.join(HERE, f"single_{kind}.npz"), **run_single(kind))
     for solver in (1, 2, 3):

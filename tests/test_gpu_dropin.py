@@ -49,7 +49,13 @@ def test_amore_entry_points(name, fn, n_out):
         assert "Number of equations = %d." % len(d["red_rhs"]) in log
         assert "Number of entries = %d." % len(d["red_data"]) in log
     if name == "AMOREBracket":
-        # shipped golden output of the reference: solution.txt:1118 "strain ENERGY 1.061718786130466e+00"
+        # the reference's shipped golden output (solution.txt: 1111 x 2 displacements + strain energy)
+        import os
+        from conftest import GOLDEN
+        from mofem_b200 import solution_io
+        g = dict(np.load(os.path.join(GOLDEN, "shipped_solution_AMOREBracket.npz")))
+        du, de = solution_io.compare(out[0], out[1], g["displacement"], g["energy"])
+        assert du <= TOL and de <= TOL
         assert abs(out[1][0][0] - 1.061718786130466e+00) <= TOL * 1.061718786130466e+00
     if name == "simpleOFE3":
         assert abs(out[1][0][0] - 19.2) <= 1e-8 * 19.2          # analytic patch-test energy
