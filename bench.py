@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events inside the PCG loop")
     ap.add_argument("--l2-persist", type=int, default=1, help="pin the PCG vectors in L2 (library default: 1)")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
+    ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything else a library prints to fd 1 (e.g. NCCL's version banner) goes
     # to stderr for the rest of the run
@@ -233,13 +236,13 @@ def main():
     part = None
     n_cells_global = None
     if world == 1:
-        fp, rhs, fixed, val = patch_family(args.n0)
+        fp, rhs, fixed, val = patch_family(args.n0, n_mesh=args.meshes)
     else:
         from mofem_b200.distributed import init_comm
         from mofem_b200.partition import exchange_send_lists, partition_problem
         ny = args.n0 * world
         per = args.n0 // 8
-        strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per))
+        strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per), n_mesh=args.meshes)
         n_node0 = (args.n0 + 1) * (ny + 1)
         owner = np.empty(strip.n_node, np.int32)
         owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // args.n0, world - 1)
@@ -292,10 +295,17 @@ def main():
     maxit = 400000
     last = {}
 
+    transport = "none"
+    if part is not None:
+        from mofem_b200.distributed import setup_peer_transport
+        ctx.set_halo(part)           # the halo plan (and the peer transport) persist across problems of the same shape
+        transport = "nccl"
+        if args.transport == "peer" and setup_peer_transport(ctx, part):
+            transport = "peer"
+        log(f"[rank {rank}] transport: {transport}")
+
     def step_resident():
         ctx.set_problem(fp_dev).symbolic().assemble()
-        if part is not None:
-            ctx.set_halo(part)
         ctx.set_system(rhs_d, fixed_d, val_d)
         _, si = ctx.solve(rtol=args.rtol, maxit=maxit, out=u_d)
         last["solve"] = si
@@ -346,7 +356,6 @@ def main():
                                                      host_sys["val"].numpy(), rtol=args.rtol, maxit=maxit)
         else:   # same calls, host buffers in / host displacement out, on every rank
             ctx.set_problem(fp_host).symbolic().assemble()
-            ctx.set_halo(part)
             ctx.set_system(host_sys["rhs"].numpy(), host_sys["fixed"].numpy(), host_sys["val"].numpy())
             u_h, si_h = ctx.solve(rtol=args.rtol, maxit=maxit)
             energy_h = ctx.energy()
@@ -399,13 +408,13 @@ def main():
         "metric": METRIC, "value": cells_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "syn-1M patch-family overlay (2 meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
+        "config": {"workload": f"syn-1M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
                    "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
                    "nnz": info["nnz"], "rtol_true_residual": args.rtol,
                    "l2": "inputs larger than L2 (CSR 0.45 GB, block values 1.6 GB vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else
-                   f"{world} GPUs: cells sharded by strip (no assembly exchange), row-partitioned PCG with NCCL halo "
-                   f"exchange + all-reduce; global problem {args.n0} x {args.n0 * world} mesh-0 elements, one corner load per block",
+                   f"{world} GPUs: cells sharded by strip (no assembly exchange), row-partitioned PCG, halo "
+                   f"exchange + all-reduce over {transport}; global problem {args.n0} x {args.n0 * world} mesh-0 elements, one corner load per block",
                    "cells_global": cells_total},
         "e2e": {"value": cells_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_s * 1e3},

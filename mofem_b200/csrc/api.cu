@@ -116,6 +116,8 @@ static double toc(mofem_ctx *ctx)
 
 extern "C" {
 
+static void p2p_close(mofem_ctx *ctx);
+
 const char *mofem_version(void) { return "mofem_b200 0.1.0 (sm_100a)"; }
 
 int mofem_create(mofem_ctx **out, int device)
@@ -151,6 +153,7 @@ void mofem_destroy(mofem_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_pool(ctx, ctx->problem_allocs); free_pool(ctx, ctx->sym_allocs); free_pool(ctx, ctx->sys_allocs);
+    p2p_close(ctx);
     free_pool(ctx, ctx->dist_allocs);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->dist.comm && nccl_api()) nccl_api()->CommDestroy(ctx->dist.comm);
@@ -447,7 +450,7 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
         ctx->slab = slab; ctx->slab_hot_bytes = sizeof(double) * (size_t)(5 * npad);
         if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
-            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &W.counters, 4, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;
@@ -607,6 +610,7 @@ int mofem_set_halo(mofem_ctx *ctx, int64_t n_owned_node, int32_t n_neighbor, con
 {
     if (!ctx) return MOFEM_E_ARG;
     CK(cudaSetDevice(ctx->device));
+    p2p_close(ctx);
     free_pool(ctx, ctx->dist_allocs);
     ctx->have_halo = false;
     ctx->have_system = ctx->have_solution = false;
@@ -628,9 +632,109 @@ int mofem_set_halo(mofem_ctx *ctx, int64_t n_owned_node, int32_t n_neighbor, con
     return MOFEM_OK;
 }
 
+static void p2p_close(mofem_ctx *ctx)
+{
+    DistPlan &D = ctx->dist;
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < (int)D.peer_host.size(); r++)
+        if (r != D.rank && D.peer_host[r]) cudaIpcCloseMemHandle(D.peer_host[r]);
+    D.peer_host.clear();
+    if (D.xbuf) cudaFree(D.xbuf);
+    if (D.peer) cudaFree(D.peer);
+    if (D.send_nb) cudaFree(D.send_nb);
+    if (D.send_dst) cudaFree(D.send_dst);
+    if (D.nb_ghost_off) cudaFree(D.nb_ghost_off);
+    if (D.nb_rank_dev) cudaFree(D.nb_rank_dev);
+    if (D.wait_rank) cudaFree(D.wait_rank);
+    D.xbuf = nullptr; D.peer = nullptr; D.send_nb = nullptr; D.send_dst = nullptr; D.nb_ghost_off = nullptr;
+    D.nb_rank_dev = nullptr; D.wait_rank = nullptr; D.n_wait = 0;
+    D.p2p = false;
+    cudaGetLastError();
+}
+
+int mofem_p2p_export(mofem_ctx *ctx, uint8_t handle[64], int64_t *n_ghost)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    if (!ctx || !handle || !n_ghost) return MOFEM_E_ARG;
+    if (!ctx->have_halo || !ctx->dist.comm) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_p2p_export: call mofem_dist_init and mofem_set_halo first");
+    CK(cudaSetDevice(ctx->device));
+    p2p_close(ctx);
+    DistPlan &D = ctx->dist;
+    D.n_ghost = D.recv_ptr.back();
+    const size_t bytes = sizeof(double) * (size_t)p2p_buffer_doubles(D.world, D.n_ghost);
+    CK(cudaMalloc(&D.xbuf, bytes));        // plain cudaMalloc: pool memory cannot be exported through legacy IPC handles
+    CK(cudaMemset(D.xbuf, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, D.xbuf));
+    memcpy(handle, &h, 64);
+    *n_ghost = D.n_ghost;
+    return MOFEM_OK;
+}
+
+int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles, const int64_t *peer_n_ghost, const int64_t *send_remote_off)
+{
+    if (!ctx || !handles || !peer_n_ghost) return MOFEM_E_ARG;
+    DistPlan &D = ctx->dist;
+    if (!D.xbuf) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_p2p_import: call mofem_p2p_export first");
+    CK(cudaSetDevice(ctx->device));
+    const int W = D.world, n_nb = (int)D.nb_rank.size();
+    if (n_nb && !send_remote_off) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_p2p_import: null send_remote_off");
+    D.peer_host.assign(W, nullptr);
+    for (int r = 0; r < W; r++) {
+        if (r == D.rank) { D.peer_host[r] = D.xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p2p_close(ctx);
+            return ctx_fail(ctx, MOFEM_E_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        }
+        D.peer_host[r] = (double *)p;
+    }
+    const int64_t n_send = D.send_ptr.back();
+    std::vector<int32_t> nb_of((size_t)n_send);
+    std::vector<int64_t> dst((size_t)n_send), goff((size_t)2 * std::max(n_nb, 1));
+    std::vector<int> wait;
+    for (int k = 0; k < n_nb; k++) {
+        for (int64_t i = D.send_ptr[k]; i < D.send_ptr[k + 1]; i++) { nb_of[i] = k; dst[i] = i - D.send_ptr[k]; }
+        for (int q = 0; q < 2; q++)
+            goff[(size_t)q * n_nb + k] = p2p_ghost_off(W, peer_n_ghost[D.nb_rank[k]], q) + 2 * send_remote_off[k];
+        if (D.recv_ptr[k + 1] > D.recv_ptr[k]) wait.push_back(D.nb_rank[k]);
+    }
+    D.send_remote_off.assign(send_remote_off, send_remote_off + n_nb);
+    D.n_wait = (int)wait.size();
+    CK(cudaMalloc(&D.peer, sizeof(double *) * W));
+    CK(cudaMalloc(&D.send_nb, sizeof(int32_t) * std::max<int64_t>(n_send, 1)));
+    CK(cudaMalloc(&D.send_dst, sizeof(int64_t) * std::max<int64_t>(n_send, 1)));
+    CK(cudaMalloc(&D.nb_ghost_off, sizeof(int64_t) * goff.size()));
+    CK(cudaMalloc(&D.nb_rank_dev, sizeof(int) * std::max(n_nb, 1)));
+    CK(cudaMalloc(&D.wait_rank, sizeof(int) * std::max(D.n_wait, 1)));
+    CK(cudaMemcpy(D.peer, D.peer_host.data(), sizeof(double *) * W, cudaMemcpyHostToDevice));
+    if (n_send) {
+        CK(cudaMemcpy(D.send_nb, nb_of.data(), sizeof(int32_t) * n_send, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(D.send_dst, dst.data(), sizeof(int64_t) * n_send, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(D.nb_ghost_off, goff.data(), sizeof(int64_t) * goff.size(), cudaMemcpyHostToDevice));
+    if (n_nb) CK(cudaMemcpy(D.nb_rank_dev, D.nb_rank.data(), sizeof(int) * n_nb, cudaMemcpyHostToDevice));
+    if (D.n_wait) CK(cudaMemcpy(D.wait_rank, wait.data(), sizeof(int) * D.n_wait, cudaMemcpyHostToDevice));
+    D.epoch = 0;
+    D.p2p = true;
+    return MOFEM_OK;
+}
+
+int mofem_p2p_close(mofem_ctx *ctx)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    p2p_close(ctx);
+    return MOFEM_OK;
+}
+
 int mofem_clear_halo(mofem_ctx *ctx)
 {
     if (!ctx) return MOFEM_E_ARG;
+    p2p_close(ctx);
     free_pool(ctx, ctx->dist_allocs);
     ctx->have_halo = false;
     ctx->have_system = ctx->have_solution = false;

@@ -113,7 +113,38 @@ struct DistPlan {
     std::vector<int64_t> send_ptr, recv_ptr;   // [n_nb + 1], in nodes; recv offsets are relative to the ghost segment
     int32_t *send_idx = nullptr;               // device: owned local node ids to send, neighbour by neighbour
     double *sendbuf = nullptr;                 // device: 2 doubles per sent node
+    // ---- NVLink peer-memory path (optional; set up by mofem_p2p_export / mofem_p2p_import) ----------------
+    bool p2p = false;
+    double *xbuf = nullptr;                    // this rank's exchange buffer (cudaMalloc, IPC-exported)
+    std::vector<double *> peer_host;           // every rank's exchange buffer mapped into this process
+    double **peer = nullptr;                   // device copy of peer_host
+    int64_t n_ghost = 0;                       // ghost nodes of this rank (capacity of the halo area)
+    std::vector<int64_t> send_remote_off;      // per neighbour: where this rank's entries start in ITS ghost segment
+    int32_t *send_nb = nullptr;                // device [n_send]: neighbour slot of every sent node
+    int64_t *send_dst = nullptr;               // device [n_send]: index inside this rank's segment of the neighbour's halo area
+    int64_t *nb_ghost_off = nullptr;           // device [2][n_nb]: offset (doubles) of that segment in the neighbour's buffer, per parity
+    int *nb_rank_dev = nullptr;                // device [n_nb]
+    int *wait_rank = nullptr;                  // device [n_wait]: ranks this rank receives ghosts from
+    int n_wait = 0;
+    int64_t epoch = 0;                         // solves done on the peer path (stamps are unique per solve)
 };
+
+// Exchange-buffer layout (doubles), identical on every rank (world = W, G = ghost-node capacity of the OWNER):
+//   mailbox  [site 0..1][parity 0..1][src rank][4] = {v0, v1, stamp, -}     16 W doubles
+//   hflag    [parity 0..1][src rank]                                          2 W doubles
+//   ghosts   [parity 0..1][2 G]                                               4 G doubles
+struct P2PDev {
+    double *const *peer;   // device array [world]
+    double *local;         // == peer[rank]
+    int world, rank;
+    double stamp;          // stamp of the CURRENT iteration (epoch * 2^32 + it + 1)
+    int parity;            // it & 1
+    int *err;              // set to 1 when a wait times out
+};
+__host__ __device__ inline int64_t p2p_mbox_off(int W, int site, int parity, int src) { return ((int64_t)(site * 2 + parity) * W + src) * 4; }
+__host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 16 * (int64_t)W + (int64_t)parity * W + src; }
+__host__ __device__ inline int64_t p2p_ghost_off(int W, int64_t G, int parity) { return 18 * (int64_t)W + (int64_t)parity * 2 * G; }
+inline int64_t p2p_buffer_doubles(int W, int64_t G) { return 18 * (int64_t)W + 4 * G + 8; }
 
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
 
@@ -122,7 +153,7 @@ struct PcgBuffers {
     double *x, *r, *p, *q, *dinv, *b, *ufix;  // n each
     double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
     double *sc;                                // 8 scalars
-    unsigned int *counters;                    // 4 arrival counters of the grid-wide reductions
+    unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = peer time-out flag
 };
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
                       PcgBuffers &w, const DistPlan *dist, cudaStream_t s, int64_t *launches);

@@ -69,14 +69,76 @@ __device__ __forceinline__ bool grid_sum(double partial, double *__restrict__ pa
     return true;
 }
 
+// ---- NVLink peer-memory primitives (row-partitioned solve, one process per GPU) ---------------------------------
+// Every rank owns an exchange buffer that all peers map (CUDA IPC).  A value travels as {payload, stamp}: the writer
+// stores the payload into the consumer's buffer, fences at system scope, then stores the stamp; the consumer polls the
+// stamp in its OWN memory.  Stamps grow monotonically (epoch, iteration), two parity slots make reuse safe: a rank can
+// only be two rounds ahead of a peer after that peer has consumed the older round.
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ bool p2p_wait(const volatile double *flag, double stamp, int *err)
+{
+    if (*flag == stamp) return true;
+    const unsigned long long t0 = global_ns();
+    while (*flag != stamp) {
+        if (global_ns() - t0 > 10000000000ull) { *err = 1; return false; }   // 10 s: a peer died -- give up, report
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// all-reduce, producer side: called by ONE block after it holds this rank's partial(s)
+__device__ __forceinline__ void p2p_publish(const P2PDev &pp, int site, double v0, double v1)
+{
+    if ((int)threadIdx.x < pp.world) {
+        double *slot = pp.peer[threadIdx.x] + p2p_mbox_off(pp.world, site, pp.parity, pp.rank);
+        slot[0] = v0; slot[1] = v1;
+        __threadfence_system();
+        *reinterpret_cast<volatile double *>(slot + 2) = pp.stamp;
+    }
+}
+
+// all-reduce, consumer side: every block sums the W partials in rank order (bit-identical on every rank and block)
+__device__ __forceinline__ void p2p_collect(const P2PDev &pp, int site, double &v0, double &v1)
+{
+    __shared__ double sv[2][64];
+    if ((int)threadIdx.x < pp.world) {
+        const double *slot = pp.local + p2p_mbox_off(pp.world, site, pp.parity, threadIdx.x);
+        p2p_wait(reinterpret_cast<const volatile double *>(slot + 2), pp.stamp, pp.err);
+        __threadfence_system();
+        sv[0][threadIdx.x] = *reinterpret_cast<const volatile double *>(slot);
+        sv[1][threadIdx.x] = *reinterpret_cast<const volatile double *>(slot + 1);
+    }
+    __syncthreads();
+    double a = 0.0, c = 0.0;
+    for (int r = 0; r < pp.world; r++) { a += sv[0][r]; c += sv[1][r]; }
+    v0 = a; v1 = c;
+    __syncthreads();
+}
+
 // y = K x on node rows; fixed rows -> 0.  Optionally the dot product x.y goes to *dot_out.
-template <bool DOT>
+// Columns >= n_split are ghosts, read from xg (the ghost segment of x, or the peer-written halo area).
+// P2P: wait for the neighbours' halo stamps before touching ghosts; publish the dot-product partial to every peer.
+template <bool DOT, bool P2P>
 __global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
-       const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out)
+       const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
+       int n_split, const double2 *xg, P2PDev pp, int n_wait, const int *__restrict__ wait_rank)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
+    if (P2P) {
+        if ((int)threadIdx.x < n_wait)
+            p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+                     pp.stamp, pp.err);
+        __syncthreads();
+        __threadfence_system();
+    }
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
     double dot = 0.0;
@@ -97,7 +159,7 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
                         const int c = __ldg(node_idx + r0 + kk);
                         v0[u] = __ldcs(d0 + kk);
                         v1[u] = __ldcs(d1 + kk);
-                        xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
+                        xv[u] = c < n_split ? __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c)) : __ldcg(xg + (c - n_split));
                     } else {
                         v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
                     }
@@ -130,7 +192,10 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
     if (DOT) {
         const double s = block_sum(dot, sm);
         double total;
-        if (grid_sum(s, part_dot, counter, sm, total) && threadIdx.x == 0) *dot_out = total;
+        if (grid_sum(s, part_dot, counter, sm, total)) {
+            if (P2P) p2p_publish(pp, 0, total, 0.0);
+            else if (threadIdx.x == 0) *dot_out = total;
+        }
     }
 }
 
@@ -213,13 +278,16 @@ __global__ void k_pcg_init_finish(double *__restrict__ sc, int keep_x)
 }
 
 // x += alpha p ; r -= alpha q ; rz_new = r.dinv.r, rr = r.r      (alpha = rz / p.q)
+template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ p, const double2 *__restrict__ q,
              const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r,
-             double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter)
+             double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp)
 {
     __shared__ double sm[VEC_BLOCK / 32];
-    const double pq = sc[SC_PQ];
+    double pq, unused;
+    if (P2P) p2p_collect(pp, 0, pq, unused);
+    else pq = sc[SC_PQ];
     const double rz_old = sc[sc_rz(it)];
     const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
     double rz = 0.0, rr = 0.0;
@@ -236,17 +304,26 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
     const double s1 = block_sum(rz, sm);
     const double s2 = block_sum(rr, sm);
     double a, c;
-    if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c) && threadIdx.x == 0) {
-        sc[sc_rz(it + 1)] = a; sc[sc_rr(it + 1)] = c;
+    if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c)) {
+        if (P2P) p2p_publish(pp, 1, a, c);
+        else if (threadIdx.x == 0) { sc[sc_rz(it + 1)] = a; sc[sc_rr(it + 1)] = c; }
     }
 }
 
 // p = dinv*r + beta p      (beta = rz_new / rz_old)
+template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
-k_pcg_direction(int64_t n2, int it, const double *__restrict__ sc, const double2 *__restrict__ r,
-                const double2 *__restrict__ dinv, double2 *__restrict__ p)
+k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
+                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp)
 {
-    const double rz_new = sc[sc_rz(it + 1)], rz_old = sc[sc_rz(it)];
+    double rz_new, rr;
+    if (P2P) {
+        p2p_collect(pp, 1, rz_new, rr);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr; }   // for the host poll
+    } else {
+        rz_new = sc[sc_rz(it + 1)];
+    }
+    const double rz_old = sc[sc_rz(it)];
     const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
         const double2 ri = r[i], di = dinv[i];
@@ -289,10 +366,37 @@ __global__ void k_pack_halo(int64_t n_send, const int32_t *__restrict__ send_idx
     if (i < n_send) buf[i] = v[send_idx[i]];
 }
 
+// Peer path: every sent entry goes straight into the neighbour's halo area (parity slot of the NEXT iteration); the
+// last block to finish raises this rank's flag in every neighbour's buffer.
+__global__ void __launch_bounds__(256)
+k_push_halo(int64_t n_send, const int32_t *__restrict__ send_idx, const int32_t *__restrict__ send_nb,
+            const int64_t *__restrict__ send_dst, const double2 *__restrict__ v, P2PDev pp,
+            const int64_t *__restrict__ nb_ghost_off, int n_nb, const int *__restrict__ nb_rank, unsigned int *counter)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_send) {
+        const int k = send_nb[i];
+        double2 *dst = reinterpret_cast<double2 *>(pp.peer[nb_rank[k]] + nb_ghost_off[k]) + send_dst[i];
+        *dst = v[send_idx[i]];
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        if ((int)threadIdx.x < n_nb) {
+            __threadfence_system();
+            *reinterpret_cast<volatile double *>(pp.peer[nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
 #define NCCL_OK(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return cudaErrorUnknown; } while (0)
 
-// ghost entries of `v` (local layout: owned nodes first, then ghosts grouped by owner) <- their owners' values
-static cudaError_t halo_exchange(const DistPlan *d, double *v, cudaStream_t s, int64_t *launches)
+// ghost entries (2 doubles per ghost node, grouped by owner) <- their owners' values of `v`, received into `ghost`
+static cudaError_t halo_exchange(const DistPlan *d, const double *v, double *ghost, cudaStream_t s, int64_t *launches)
 {
     if (!d || d->nb_rank.empty()) return cudaSuccess;
     const int64_t n_send = d->send_ptr.back();
@@ -307,7 +411,7 @@ static cudaError_t halo_exchange(const DistPlan *d, double *v, cudaStream_t s, i
     for (size_t k = 0; k < d->nb_rank.size(); k++) {
         const int64_t ns = d->send_ptr[k + 1] - d->send_ptr[k], nr = d->recv_ptr[k + 1] - d->recv_ptr[k];
         if (ns) NCCL_OK(nc->Send(d->sendbuf + 2 * d->send_ptr[k], (size_t)(2 * ns), ncclDouble, d->nb_rank[k], d->comm, s));
-        if (nr) NCCL_OK(nc->Recv(v + 2 * (d->n_owned_node + d->recv_ptr[k]), (size_t)(2 * nr), ncclDouble, d->nb_rank[k], d->comm, s));
+        if (nr) NCCL_OK(nc->Recv(ghost + 2 * d->recv_ptr[k], (size_t)(2 * nr), ncclDouble, d->nb_rank[k], d->comm, s));
     }
     NCCL_OK(nc->GroupEnd());
     return cudaGetLastError();
@@ -342,13 +446,24 @@ static int spmv_grid(int64_t n_node)
     return (int)g;
 }
 
+static const P2PDev NO_P2P{nullptr, nullptr, 1, 0, 0.0, 0, nullptr};
+
+// plain launch: ghosts (if any) are the tail of x
+template <bool DOT>
+static void launch_spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, double *part, unsigned int *counter,
+                        double *dot_out, cudaStream_t s)
+{
+    const int64_t n_node = A.n_own / 2;
+    k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
+                                                                 dot_out, (int)n_node, reinterpret_cast<const double2 *>(x) + n_node,
+                                                                 NO_P2P, 0, nullptr);
+}
+
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, cudaStream_t s)
 {
-    const int64_t n_node = A.n_own / 2;
-    if (n_node == 0) return cudaSuccess;
-    k_spmv<false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, nullptr,
-                                                            nullptr, nullptr);
+    if (A.n_own == 0) return cudaSuccess;
+    launch_spmv<false>(A, x, y, fixed, nullptr, nullptr, nullptr, s);
     return cudaGetLastError();
 }
 
@@ -357,7 +472,7 @@ cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed,
 {
     const int64_t n = A.n, n_own = A.n_own;
     (void)dist;  // fixed / fixed_val cover the ghost nodes too, so u_fix needs no exchange
-    cudaError_t e = cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 4, s);
+    cudaError_t e = cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 8, s);
     if (e != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w.x, 0, sizeof(double) * n, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w.p, 0, sizeof(double) * n, s)) != cudaSuccess) return e;
@@ -375,11 +490,10 @@ cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed,
 static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist,
                                  cudaStream_t s, double *rr_true, int64_t *launches)
 {
-    const int64_t n_own = A.n_own, n_node = n_own / 2;
-    cudaError_t e = halo_exchange(dist, w.x, s, launches);
+    const int64_t n_own = A.n_own;
+    cudaError_t e = halo_exchange(dist, w.x, w.x + n_own, s, launches);
     if (e != cudaSuccess) return e;
-    k_spmv<false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.x, w.q, fixed, nullptr,
-                                                            nullptr, nullptr);
+    launch_spmv<false>(A, w.x, w.q, fixed, nullptr, nullptr, nullptr, s);
     k_true_residual<<<vec_grid(n_own), VEC_BLOCK, 0, s>>>(n_own, w.b, w.q, w.r, w.part_b, w.counters + 2, w.sc + SC_RR_TRUE);
     if (launches) *launches += 2;
     if ((e = all_reduce(dist, w.sc + SC_RR_TRUE, 1, s)) != cudaSuccess) return e;
@@ -392,16 +506,36 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
 // prof (optional): 2 pools of 4*chunk events; prof_ms[0..2] accumulate the device time of the SpMV (incl. halo
 // exchange and the p.q all-reduce when row-partitioned) / update / direction kernels, prof_ms[3] the iterations
 // profiled.  The events of a chunk are read back while the next chunk runs, so profiling does not stall the GPU.
+//
+// Row-partitioned, two transports:
+//   NCCL  -- per iteration: pack + ncclSend/Recv of the ghost entries of p, ncclAllReduce(p.q), ncclAllReduce(rz, rr)
+//   peer  -- (dist->p2p) no NCCL call inside the loop: k_push_halo writes this rank's boundary entries of p into the
+//            neighbours' halo areas over NVLink, the SpMV waits for its neighbours' stamps; the last block of the
+//            SpMV / update kernel writes its partial into every peer's mailbox and the next kernel sums the W partials
+//            in rank order.  The first iteration after (re)initialisation still uses NCCL for the halo.
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist, double rtol, int maxit,
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
-    const int gv = vec_grid(n2), gd = vec_grid(n2), gs = spmv_grid(n_node);
+    const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
-    double sc_host[8];
+    double sc_host[10];
     const double2 *b2 = reinterpret_cast<const double2 *>(w.b), *dinv2 = reinterpret_cast<const double2 *>(w.dinv);
     double2 *x2 = reinterpret_cast<double2 *>(w.x), *r2 = reinterpret_cast<double2 *>(w.r);
     double2 *p2 = reinterpret_cast<double2 *>(w.p), *q2 = reinterpret_cast<double2 *>(w.q);
+    const bool peer = dist && dist->p2p && dist->world > 1;
+    const int W = dist ? dist->world : 1;
+    DistPlan *dm = const_cast<DistPlan *>(dist);
+    const double stamp0 = peer ? (double)(++dm->epoch) * 4294967296.0 : 0.0;
+    int *err_dev = reinterpret_cast<int *>(w.counters + 6);
+    auto ppdev = [&](int it_for) {
+        P2PDev pp = NO_P2P;
+        if (peer) {
+            pp.peer = dist->peer; pp.local = dist->xbuf; pp.world = W; pp.rank = dist->rank;
+            pp.stamp = stamp0 + (double)it_for + 1.0; pp.parity = it_for & 1; pp.err = err_dev;
+        }
+        return pp;
+    };
     auto init = [&](int keep_x) -> cudaError_t {
         k_pcg_init<<<gv, VEC_BLOCK, 0, s>>>(n2, b2, dinv2, x2, r2, p2, w.part_a, w.part_b, w.counters + 1, w.sc, keep_x);
         cudaError_t ee = all_reduce(dist, w.sc, 2, s);
@@ -424,6 +558,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
     const double tol2 = rtol * rtol * bnorm2;
     int it = 0;       // global iteration counter (parity selects the (rz, rr) pair)
     double prev_rr_true = 0.0;
+    bool fresh = true;   // p was just (re)initialised: its halo has not been pushed by a previous iteration
     int pend_pool = -1, pend_n = 0, pool = 0;
     auto harvest = [&]() {
         if (!prof || pend_pool < 0) return;
@@ -438,29 +573,62 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
         pend_pool = -1;
     };
     auto done = [&](cudaError_t ee) { harvest(); return ee; };
+    const int n_nb = dist ? (int)dist->nb_rank.size() : 0;
+    const int64_t n_send = dist && !dist->send_ptr.empty() ? dist->send_ptr.back() : 0;
     while (it < maxit) {
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
         cudaEvent_t *ev = prof ? prof + (size_t)pool * 4 * chunk : nullptr;
         for (int k = 0; k < todo; k++, it++) {
             if (ev) cudaEventRecord(ev[4 * k], s);
-            if ((e = halo_exchange(dist, w.p, s, launches)) != cudaSuccess) return done(e);
-            k_spmv<true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
-                                                   w.counters, w.sc + SC_PQ);
-            if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s)) != cudaSuccess) return done(e);
-            if (ev) cudaEventRecord(ev[4 * k + 1], s);
-            k_pcg_update<<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b, w.counters + 1);
-            if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
-            if (ev) cudaEventRecord(ev[4 * k + 2], s);
-            k_pcg_direction<<<gd, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2);
-            if (ev) cudaEventRecord(ev[4 * k + 3], s);
+            if (!peer) {
+                if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
+                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + SC_PQ, s);
+                if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s)) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                k_pcg_update<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
+                                                            w.counters + 1, NO_P2P);
+                if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 2], s);
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P);
+                if (ev) cudaEventRecord(ev[4 * k + 3], s);
+            } else {
+                const P2PDev pp = ppdev(it);
+                double *ghost = dist->xbuf + p2p_ghost_off(W, dist->n_ghost, it & 1);
+                if (fresh) {   // halo of a freshly initialised p: NCCL into this iteration's halo area, nothing to wait for
+                    if ((e = halo_exchange(dist, w.p, ghost, s, launches)) != cudaSuccess) return done(e);
+                }
+                k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
+                                                            w.counters, nullptr, (int)n_node,
+                                                            reinterpret_cast<const double2 *>(ghost), pp,
+                                                            fresh ? 0 : dist->n_wait, dist->wait_rank);
+                fresh = false;
+                if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
+                                                           w.counters + 1, pp);
+                if (ev) cudaEventRecord(ev[4 * k + 2], s);
+                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp);
+                if (n_nb) {   // boundary entries of the new p -> neighbours' halo areas of iteration it + 1
+                    const P2PDev pn = ppdev(it + 1);
+                    const unsigned gp = (unsigned)std::max<int64_t>((n_send + 255) / 256, 1);
+                    k_push_halo<<<gp, 256, 0, s>>>(n_send, dist->send_idx, dist->send_nb, dist->send_dst, p2, pn,
+                                                   dist->nb_ghost_off + (size_t)((it + 1) & 1) * n_nb, n_nb, dist->nb_rank_dev,
+                                                   w.counters + 4);
+                    if (launches) ++*launches;
+                }
+                if (ev) cudaEventRecord(ev[4 * k + 3], s);
+            }
         }
         if (launches) *launches += 3 * (int64_t)todo;
         harvest();  // events of the previous chunk, while this one runs
         e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
+        int err_host = 0;
+        if (peer) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return done(e);
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return done(e);
+        if (err_host) return done(cudaErrorLaunchTimeout);   // a peer did not answer within 10 s
         if (prof) { pend_pool = pool; pend_n = todo; pool ^= 1; }
         info->iterations = it;
         const double rr = sc_host[sc_rr(it)];
@@ -482,6 +650,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
             info->restarts++;
             if (info->restarts > 20) break;
             if ((e = init(1)) != cudaSuccess) return done(e);  // publishes rz in both parity slots
+            fresh = true;
         }
     }
     // not converged by the recurrence test: report the true residual anyway
@@ -496,7 +665,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
 // u = x + u_fix over all local DOFs (ghosts included)
 cudaError_t pcg_finish(const DevSystem &A, PcgBuffers &w, const DistPlan *dist, double *u_dev, cudaStream_t s)
 {
-    cudaError_t e = halo_exchange(dist, w.x, s, nullptr);
+    cudaError_t e = halo_exchange(dist, w.x, w.x + A.n_own, s, nullptr);
     if (e != cudaSuccess) return e;
     k_add_vec<<<(unsigned)((A.n + 255) / 256), 256, 0, s>>>(A.n, w.x, w.ufix, u_dev);
     return cudaGetLastError();
@@ -505,9 +674,7 @@ cudaError_t pcg_finish(const DevSystem &A, PcgBuffers &w, const DistPlan *dist, 
 // u^T K u  (the caller halves it); u must hold current ghost values
 cudaError_t energy_of(const DevSystem &A, const double *u, PcgBuffers &w, const DistPlan *dist, double *out_dev, cudaStream_t s)
 {
-    const int64_t n_node = A.n_own / 2;
-    k_spmv<true><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, u, w.q, nullptr, w.part_c,
-                                                          w.counters + 3, out_dev);
+    launch_spmv<true>(A, u, w.q, nullptr, w.part_c, w.counters + 3, out_dev, s);
     cudaError_t e = all_reduce(dist, out_dev, 1, s);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

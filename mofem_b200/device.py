@@ -189,6 +189,25 @@ class Context:
                                         _lib.ptr(si) if len(si) else None, _lib.ptr(rp)))
         return self
 
+    def p2p_export(self):
+        """-> (64-byte CUDA IPC handle of this rank's exchange buffer, its ghost-node capacity)."""
+        buf = (C.c_uint8 * 64)()
+        g = C.c_int64(0)
+        self._ck(self._L.mofem_p2p_export(self._h, buf, C.byref(g)))
+        return bytes(buf), int(g.value)
+
+    def p2p_import(self, handles, peer_n_ghost, send_remote_off):
+        hb = b"".join(handles)
+        hbuf = (C.c_uint8 * len(hb)).from_buffer_copy(hb)
+        ng = _c(np.asarray(peer_n_ghost), np.int64)
+        so = _c(np.asarray(send_remote_off), np.int64)
+        self._ck(self._L.mofem_p2p_import(self._h, hbuf, _lib.ptr(ng), _lib.ptr(so) if len(so) else None))
+        return self
+
+    def p2p_close(self):
+        self._ck(self._L.mofem_p2p_close(self._h))
+        return self
+
     def clear_halo(self):
         self._ck(self._L.mofem_clear_halo(self._h))
         return self

@@ -24,12 +24,38 @@ def init_comm(ctx: Context, group=None):
     return rank, world
 
 
+def setup_peer_transport(ctx: Context, part: LocalPart, group=None):
+    """Switch the PCG loop of ``ctx`` from NCCL to the NVLink peer-memory transport (after ``ctx.set_halo(part)``).
+    Collective over ``group``; returns False (and leaves NCCL in place) when CUDA IPC is not available."""
+    import torch.distributed as dist
+    handle, n_ghost = ctx.p2p_export()
+    mine = (handle, n_ghost, {int(nb): int(part.recv_ptr[k]) for k, nb in enumerate(part.neighbors)})
+    gathered = [None] * part.world
+    dist.all_gather_object(gathered, mine, group=group)
+    send_remote_off = [gathered[int(nb)][2].get(part.rank, 0) for nb in part.neighbors]
+    ok = True
+    try:
+        ctx.p2p_import([g[0] for g in gathered], [g[1] for g in gathered], send_remote_off)
+    except Exception:
+        ok = False
+    flags = [None] * part.world
+    dist.all_gather_object(flags, ok, group=group)
+    if not all(flags):          # all ranks or none
+        ctx.p2p_close()
+        return False
+    return True
+
+
 def assemble_solve_partitioned(ctx: Context, part: LocalPart, rhs_local, fixed_local, val_local, rtol=1e-10,
-                               maxit=400000, out=None):
+                               maxit=400000, out=None, transport="nccl", group=None):
     """Assembly of the local problem (no exchange) + row-partitioned Jacobi-PCG.  The three system arrays are in
-    LOCAL numbering (``part.local_vector(global)``), ghosts included.  Returns (u_local, info, global energy)."""
+    LOCAL numbering (``part.local_vector(global)``), ghosts included.  ``transport``: "nccl" or "peer" (NVLink peer
+    memory inside the kernels; collective set-up).  Returns (u_local, info, global energy)."""
     ctx.set_problem(part.fp).symbolic().assemble()
     ctx.set_halo(part)
+    if transport == "peer" and part.world > 1:
+        if not setup_peer_transport(ctx, part, group):
+            raise RuntimeError("CUDA IPC peer transport could not be set up")
     ctx.set_system(rhs_local, fixed_local, val_local)
     u, info = ctx.solve(rtol=rtol, maxit=maxit, out=out)
     return u, info, ctx.energy()

@@ -18,7 +18,7 @@ def lib_path():
 def _declared_symbols():
     text = open(os.path.join(REPO, "include", "mofem_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mofem_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(mofem_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_and_binding_agree():

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, transport):
     import torch
     import torch.distributed as dist
     from mofem_b200 import overlay_gen
@@ -39,7 +39,7 @@ def _worker(rank, world, port, out):
         with Context(rank) as ctx:
             init_comm(ctx)
             u_loc, info, energy = assemble_solve_partitioned(ctx, part, part.local_vector(rhs), part.local_vector(fixed),
-                                                             part.local_vector(val), rtol=1e-12)
+                                                             part.local_vector(val), rtol=1e-12, transport=transport)
             u = gather_global(part, u_loc, strip.n_node)
             # ghost entries of the returned local vector are current
             assert np.array_equal(u_loc, part.local_vector(u))
@@ -48,7 +48,8 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_solve_matches_single_gpu(gpu_ctx):
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
+def test_two_gpu_solve_matches_single_gpu(gpu_ctx, transport):
     import torch
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 GPUs")
@@ -63,7 +64,7 @@ def test_two_gpu_solve_matches_single_gpu(gpu_ctx):
     port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(WORLD, port, out), nprocs=WORLD, join=True)
+        mp.spawn(_worker, args=(WORLD, port, out, transport), nprocs=WORLD, join=True)
         res = [out[r] for r in range(WORLD)]
     for u, info, energy in res:
         assert info["converged"] == 1
