@@ -153,11 +153,11 @@ int mofem_clear_halo(mofem_ctx *ctx);
 /* Optional NVLink peer-memory transport for the PCG loop (replaces the per-iteration NCCL calls): every rank exports an
  * exchange buffer (CUDA IPC), imports everybody else's, and from then on mofem_solve pushes halo entries and dot-product
  * partials straight into the peers' buffers from inside its kernels.  Call after mofem_set_halo, on every rank:
- *   mofem_p2p_export -> all-gather {handle, n_ghost, recv offsets} by the caller -> mofem_p2p_import.
+ *   mofem_p2p_export -> all-gather {handle, n_owned_node, recv offsets} by the caller -> mofem_p2p_import.
  * send_remote_off[k] = offset (nodes) of this rank's entries inside neighbour k's ghost segment (its recv_ptr for us).
  * A new mofem_set_halo / mofem_clear_halo drops the transport; mofem_solve then falls back to NCCL. */
 int mofem_p2p_export(mofem_ctx *ctx, uint8_t handle[64], int64_t *n_ghost);
-int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles /* world x 64 */, const int64_t *peer_n_ghost /* world */,
+int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles /* world x 64 */, const int64_t *peer_n_owned /* world */,
                      const int64_t *send_remote_off /* n_neighbor */);
 int mofem_p2p_close(mofem_ctx *ctx);
 

@@ -661,7 +661,7 @@ int mofem_p2p_export(mofem_ctx *ctx, uint8_t handle[64], int64_t *n_ghost)
     p2p_close(ctx);
     DistPlan &D = ctx->dist;
     D.n_ghost = D.recv_ptr.back();
-    const size_t bytes = sizeof(double) * (size_t)p2p_buffer_doubles(D.world, D.n_ghost);
+    const size_t bytes = sizeof(double) * (size_t)p2p_buffer_doubles(D.world, D.n_owned_node + D.n_ghost);
     CK(cudaMalloc(&D.xbuf, bytes));        // plain cudaMalloc: pool memory cannot be exported through legacy IPC handles
     CK(cudaMemset(D.xbuf, 0, bytes));
     cudaIpcMemHandle_t h;
@@ -671,9 +671,9 @@ int mofem_p2p_export(mofem_ctx *ctx, uint8_t handle[64], int64_t *n_ghost)
     return MOFEM_OK;
 }
 
-int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles, const int64_t *peer_n_ghost, const int64_t *send_remote_off)
+int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles, const int64_t *peer_n_owned, const int64_t *send_remote_off)
 {
-    if (!ctx || !handles || !peer_n_ghost) return MOFEM_E_ARG;
+    if (!ctx || !handles || !peer_n_owned) return MOFEM_E_ARG;
     DistPlan &D = ctx->dist;
     if (!D.xbuf) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_p2p_import: call mofem_p2p_export first");
     CK(cudaSetDevice(ctx->device));
@@ -695,12 +695,12 @@ int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles, const int64_t *peer
     }
     const int64_t n_send = D.send_ptr.back();
     std::vector<int32_t> nb_of((size_t)n_send);
-    std::vector<int64_t> dst((size_t)n_send), goff((size_t)2 * std::max(n_nb, 1));
+    std::vector<int64_t> dst((size_t)n_send), goff((size_t)std::max(n_nb, 1));
     std::vector<int> wait;
     for (int k = 0; k < n_nb; k++) {
         for (int64_t i = D.send_ptr[k]; i < D.send_ptr[k + 1]; i++) { nb_of[i] = k; dst[i] = i - D.send_ptr[k]; }
-        for (int q = 0; q < 2; q++)
-            goff[(size_t)q * n_nb + k] = p2p_ghost_off(W, peer_n_ghost[D.nb_rank[k]], q) + 2 * send_remote_off[k];
+        // ghost segment of the neighbour's p = after its owned nodes; our entries start send_remote_off[k] nodes into it
+        goff[k] = p2p_p_off(W) + 2 * (peer_n_owned[D.nb_rank[k]] + send_remote_off[k]);
         if (D.recv_ptr[k + 1] > D.recv_ptr[k]) wait.push_back(D.nb_rank[k]);
     }
     D.send_remote_off.assign(send_remote_off, send_remote_off + n_nb);

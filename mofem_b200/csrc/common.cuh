@@ -122,17 +122,19 @@ struct DistPlan {
     std::vector<int64_t> send_remote_off;      // per neighbour: where this rank's entries start in ITS ghost segment
     int32_t *send_nb = nullptr;                // device [n_send]: neighbour slot of every sent node
     int64_t *send_dst = nullptr;               // device [n_send]: index inside this rank's segment of the neighbour's halo area
-    int64_t *nb_ghost_off = nullptr;           // device [2][n_nb]: offset (doubles) of that segment in the neighbour's buffer, per parity
+    int64_t *nb_ghost_off = nullptr;           // device [n_nb]: offset (doubles) of that segment in the neighbour's buffer
     int *nb_rank_dev = nullptr;                // device [n_nb]
     int *wait_rank = nullptr;                  // device [n_wait]: ranks this rank receives ghosts from
     int n_wait = 0;
     int64_t epoch = 0;                         // solves done on the peer path (stamps are unique per solve)
 };
 
-// Exchange-buffer layout (doubles), identical on every rank (world = W, G = ghost-node capacity of the OWNER):
+// Exchange-buffer layout (doubles), identical on every rank (world = W):
 //   mailbox  [site 0..1][parity 0..1][src rank][4] = {v0, v1, stamp, -}     16 W doubles
 //   hflag    [parity 0..1][src rank]                                          2 W doubles
-//   ghosts   [parity 0..1][2 G]                                               4 G doubles
+//   p        [owned nodes | ghost nodes][2]   the search direction of the PCG lives HERE on the peer path, so that
+//            neighbours write their boundary entries straight into its ghost segment and the SpMV gathers from one
+//            contiguous vector
 struct P2PDev {
     double *const *peer;   // device array [world]
     double *local;         // == peer[rank]
@@ -143,8 +145,8 @@ struct P2PDev {
 };
 __host__ __device__ inline int64_t p2p_mbox_off(int W, int site, int parity, int src) { return ((int64_t)(site * 2 + parity) * W + src) * 4; }
 __host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 16 * (int64_t)W + (int64_t)parity * W + src; }
-__host__ __device__ inline int64_t p2p_ghost_off(int W, int64_t G, int parity) { return 18 * (int64_t)W + (int64_t)parity * 2 * G; }
-inline int64_t p2p_buffer_doubles(int W, int64_t G) { return 18 * (int64_t)W + 4 * G + 8; }
+__host__ __device__ inline int64_t p2p_p_off(int W) { return 18 * (int64_t)W; }
+inline int64_t p2p_buffer_doubles(int W, int64_t n_local_node) { return 18 * (int64_t)W + 2 * n_local_node + 8; }
 
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
 

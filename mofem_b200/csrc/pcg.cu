@@ -122,14 +122,14 @@ __device__ __forceinline__ void p2p_collect(const P2PDev &pp, int site, double &
 }
 
 // y = K x on node rows; fixed rows -> 0.  Optionally the dot product x.y goes to *dot_out.
-// Columns >= n_split are ghosts, read from xg (the ghost segment of x, or the peer-written halo area).
+// Ghost columns are the tail of x.
 // P2P: wait for the neighbours' halo stamps before touching ghosts; publish the dot-product partial to every peer.
 template <bool DOT, bool P2P>
 __global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
        const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
-       int n_split, const double2 *xg, P2PDev pp, int n_wait, const int *__restrict__ wait_rank)
+       P2PDev pp, int n_wait, const int *__restrict__ wait_rank)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
     if (P2P) {
@@ -159,7 +159,10 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
                         const int c = __ldg(node_idx + r0 + kk);
                         v0[u] = __ldcs(d0 + kk);
                         v1[u] = __ldcs(d1 + kk);
-                        xv[u] = c < n_split ? __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c)) : __ldcg(xg + (c - n_split));
+                        // peer path: the ghost segment of x is written by other GPUs during this kernel's lifetime
+                        // (before their stamp), so the gather must not use the non-coherent path: L2 loads
+                        if (P2P) xv[u] = __ldcg(reinterpret_cast<const double2 *>(x) + c);
+                        else xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
                     } else {
                         v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
                     }
@@ -366,8 +369,8 @@ __global__ void k_pack_halo(int64_t n_send, const int32_t *__restrict__ send_idx
     if (i < n_send) buf[i] = v[send_idx[i]];
 }
 
-// Peer path: every sent entry goes straight into the neighbour's halo area (parity slot of the NEXT iteration); the
-// last block to finish raises this rank's flag in every neighbour's buffer.
+// Peer path: every sent entry goes straight into the ghost segment of the neighbour's search direction; the last block to
+// finish raises this rank's flag (parity slot of the NEXT iteration) in every neighbour's buffer.
 __global__ void __launch_bounds__(256)
 k_push_halo(int64_t n_send, const int32_t *__restrict__ send_idx, const int32_t *__restrict__ send_nb,
             const int64_t *__restrict__ send_dst, const double2 *__restrict__ v, P2PDev pp,
@@ -455,8 +458,7 @@ static void launch_spmv(const DevSystem &A, const double *x, double *y, const ui
 {
     const int64_t n_node = A.n_own / 2;
     k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
-                                                                 dot_out, (int)n_node, reinterpret_cast<const double2 *>(x) + n_node,
-                                                                 NO_P2P, 0, nullptr);
+                                                                 dot_out, NO_P2P, 0, nullptr);
 }
 
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
@@ -513,9 +515,10 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
 //            neighbours' halo areas over NVLink, the SpMV waits for its neighbours' stamps; the last block of the
 //            SpMV / update kernel writes its partial into every peer's mailbox and the next kernel sums the W partials
 //            in rank order.  The first iteration after (re)initialisation still uses NCCL for the halo.
-cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist, double rtol, int maxit,
+cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, const DistPlan *dist, double rtol, int maxit,
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
+    PcgBuffers w = w_in;   // local copy: the peer path redirects p into the exchange buffer
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
     const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
@@ -524,6 +527,10 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
     double2 *x2 = reinterpret_cast<double2 *>(w.x), *r2 = reinterpret_cast<double2 *>(w.r);
     double2 *p2 = reinterpret_cast<double2 *>(w.p), *q2 = reinterpret_cast<double2 *>(w.q);
     const bool peer = dist && dist->p2p && dist->world > 1;
+    if (peer) {   // the search direction lives in the exchange buffer (neighbours write its ghost segment)
+        w.p = dist->xbuf + p2p_p_off(dist->world);
+        p2 = reinterpret_cast<double2 *>(w.p);
+    }
     const int W = dist ? dist->world : 1;
     DistPlan *dm = const_cast<DistPlan *>(dist);
     const double stamp0 = peer ? (double)(++dm->epoch) * 4294967296.0 : 0.0;
@@ -594,14 +601,11 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             } else {
                 const P2PDev pp = ppdev(it);
-                double *ghost = dist->xbuf + p2p_ghost_off(W, dist->n_ghost, it & 1);
-                if (fresh) {   // halo of a freshly initialised p: NCCL into this iteration's halo area, nothing to wait for
-                    if ((e = halo_exchange(dist, w.p, ghost, s, launches)) != cudaSuccess) return done(e);
+                if (fresh) {   // halo of a freshly initialised p: NCCL, nothing to wait for
+                    if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
                 }
                 k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
-                                                            w.counters, nullptr, (int)n_node,
-                                                            reinterpret_cast<const double2 *>(ghost), pp,
-                                                            fresh ? 0 : dist->n_wait, dist->wait_rank);
+                                                            w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank);
                 fresh = false;
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
@@ -612,7 +616,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, con
                     const P2PDev pn = ppdev(it + 1);
                     const unsigned gp = (unsigned)std::max<int64_t>((n_send + 255) / 256, 1);
                     k_push_halo<<<gp, 256, 0, s>>>(n_send, dist->send_idx, dist->send_nb, dist->send_dst, p2, pn,
-                                                   dist->nb_ghost_off + (size_t)((it + 1) & 1) * n_nb, n_nb, dist->nb_rank_dev,
+                                                   dist->nb_ghost_off, n_nb, dist->nb_rank_dev,
                                                    w.counters + 4);
                     if (launches) ++*launches;
                 }

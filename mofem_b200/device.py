@@ -196,10 +196,10 @@ class Context:
         self._ck(self._L.mofem_p2p_export(self._h, buf, C.byref(g)))
         return bytes(buf), int(g.value)
 
-    def p2p_import(self, handles, peer_n_ghost, send_remote_off):
+    def p2p_import(self, handles, peer_n_owned, send_remote_off):
         hb = b"".join(handles)
         hbuf = (C.c_uint8 * len(hb)).from_buffer_copy(hb)
-        ng = _c(np.asarray(peer_n_ghost), np.int64)
+        ng = _c(np.asarray(peer_n_owned), np.int64)
         so = _c(np.asarray(send_remote_off), np.int64)
         self._ck(self._L.mofem_p2p_import(self._h, hbuf, _lib.ptr(ng), _lib.ptr(so) if len(so) else None))
         return self

@@ -29,7 +29,7 @@ def setup_peer_transport(ctx: Context, part: LocalPart, group=None):
     Collective over ``group``; returns False (and leaves NCCL in place) when CUDA IPC is not available."""
     import torch.distributed as dist
     handle, n_ghost = ctx.p2p_export()
-    mine = (handle, n_ghost, {int(nb): int(part.recv_ptr[k]) for k, nb in enumerate(part.neighbors)})
+    mine = (handle, int(part.n_owned_node), {int(nb): int(part.recv_ptr[k]) for k, nb in enumerate(part.neighbors)})
     gathered = [None] * part.world
     dist.all_gather_object(gathered, mine, group=group)
     send_remote_off = [gathered[int(nb)][2].get(part.rank, 0) for nb in part.neighbors]
