@@ -74,20 +74,15 @@ __device__ __forceinline__ bool grid_sum(double partial, double *__restrict__ pa
 // stores the payload into the consumer's buffer, fences at system scope, then stores the stamp; the consumer polls the
 // stamp in its OWN memory.  Stamps grow monotonically (epoch, iteration), two parity slots make reuse safe: a rank can
 // only be two rounds ahead of a peer after that peer has consumed the older round.
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 __device__ __forceinline__ bool p2p_wait(const volatile double *flag, double stamp, int *err)
 {
-    if (*flag == stamp) return true;
-    const unsigned long long t0 = global_ns();
-    while (*flag != stamp) {
-        if (global_ns() - t0 > 10000000000ull) { *err = 1; return false; }   // 10 s: a peer died -- give up, report
-        __nanosleep(64);
+    long long t0 = 0;
+    for (unsigned spins = 0; *flag != stamp; spins++) {
+        if ((spins & 0xfff) == 0xfff) {          // look at the clock every 4096 polls: 20 s at ~2 GHz -> a peer died
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 40000000000ll) { *err = 1; return false; }
+        }
     }
     return true;
 }
@@ -133,11 +128,12 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
 {
     __shared__ double sm[SPMV_BLOCK / 32];
     if (P2P) {
-        if ((int)threadIdx.x < n_wait)
+        if ((int)threadIdx.x < n_wait) {
             p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
                      pp.stamp, pp.err);
+            __threadfence_system();
+        }
         __syncthreads();
-        __threadfence_system();
     }
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
@@ -159,10 +155,10 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
                         const int c = __ldg(node_idx + r0 + kk);
                         v0[u] = __ldcs(d0 + kk);
                         v1[u] = __ldcs(d1 + kk);
-                        // peer path: the ghost segment of x is written by other GPUs during this kernel's lifetime
-                        // (before their stamp), so the gather must not use the non-coherent path: L2 loads
-                        if (P2P) xv[u] = __ldcg(reinterpret_cast<const double2 *>(x) + c);
-                        else xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
+                        // peer path: the ghost segment of x is written by other GPUs before their stamp arrives; no block
+                        // reads it before its own wait below has passed and L1 starts empty at kernel launch, so the
+                        // cached read-only path is safe here too
+                        xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
                     } else {
                         v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
                     }
@@ -314,10 +310,21 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
 }
 
 // p = dinv*r + beta p      (beta = rz_new / rz_old)
+struct HaloPush {          // peer path: what the direction kernel needs to deliver the new p to the neighbours
+    int64_t n_send;
+    const int32_t *send_idx, *send_nb;
+    const int64_t *send_dst, *nb_ghost_off;
+    const int *nb_rank;
+    int n_nb;
+    unsigned int *counter;
+    double stamp_next;     // stamp / parity of iteration it + 1
+    int parity_next;
+};
+
 template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
-                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp)
+                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, HaloPush hp)
 {
     double rz_new, rr;
     if (P2P) {
@@ -333,6 +340,28 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
         double2 pi = p[i];
         pi.x = fma(beta, pi.x, di.x * ri.x); pi.y = fma(beta, pi.y, di.y * ri.y);
         p[i] = pi;
+    }
+    if (P2P && hp.n_nb) {
+        // the last block to finish knows p is complete: it writes this rank's boundary entries into the ghost segment of
+        // the neighbours' p over NVLink and then raises its flag there (fused compute + halo exchange, no extra launch)
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = (atomicAdd(hp.counter, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            for (int64_t i = threadIdx.x; i < hp.n_send; i += blockDim.x) {
+                const int k = hp.send_nb[i];
+                double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
+                *dst = __ldcg(p + hp.send_idx[i]);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < hp.n_nb)
+                *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, hp.parity_next, pp.rank)) = hp.stamp_next;
+            if (threadIdx.x == 0) *hp.counter = 0u;
+        }
     }
 }
 
@@ -367,33 +396,6 @@ __global__ void k_pack_halo(int64_t n_send, const int32_t *__restrict__ send_idx
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_send) buf[i] = v[send_idx[i]];
-}
-
-// Peer path: every sent entry goes straight into the ghost segment of the neighbour's search direction; the last block to
-// finish raises this rank's flag (parity slot of the NEXT iteration) in every neighbour's buffer.
-__global__ void __launch_bounds__(256)
-k_push_halo(int64_t n_send, const int32_t *__restrict__ send_idx, const int32_t *__restrict__ send_nb,
-            const int64_t *__restrict__ send_dst, const double2 *__restrict__ v, P2PDev pp,
-            const int64_t *__restrict__ nb_ghost_off, int n_nb, const int *__restrict__ nb_rank, unsigned int *counter)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_send) {
-        const int k = send_nb[i];
-        double2 *dst = reinterpret_cast<double2 *>(pp.peer[nb_rank[k]] + nb_ghost_off[k]) + send_dst[i];
-        *dst = v[send_idx[i]];
-    }
-    __threadfence_system();
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (last) {
-        if ((int)threadIdx.x < n_nb) {
-            __threadfence_system();
-            *reinterpret_cast<volatile double *>(pp.peer[nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
-    }
 }
 
 #define NCCL_OK(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return cudaErrorUnknown; } while (0)
@@ -597,7 +599,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                                                             w.counters + 1, NO_P2P);
                 if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P);
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, HaloPush{});
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             } else {
                 const P2PDev pp = ppdev(it);
@@ -611,15 +613,11 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
                                                            w.counters + 1, pp);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp);
-                if (n_nb) {   // boundary entries of the new p -> neighbours' halo areas of iteration it + 1
-                    const P2PDev pn = ppdev(it + 1);
-                    const unsigned gp = (unsigned)std::max<int64_t>((n_send + 255) / 256, 1);
-                    k_push_halo<<<gp, 256, 0, s>>>(n_send, dist->send_idx, dist->send_nb, dist->send_dst, p2, pn,
-                                                   dist->nb_ghost_off, n_nb, dist->nb_rank_dev,
-                                                   w.counters + 4);
-                    if (launches) ++*launches;
-                }
+                HaloPush hp{};
+                hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
+                hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb; hp.counter = w.counters + 4;
+                hp.stamp_next = stamp0 + (double)(it + 1) + 1.0; hp.parity_next = (it + 1) & 1;
+                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp, hp);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             }
         }
