@@ -130,7 +130,7 @@ struct DistPlan {
 };
 
 // Exchange-buffer layout (doubles), identical on every rank (world = W):
-//   mailbox  [site 0..1][parity 0..1][src rank][4] = {v0, v1, stamp, -}     16 W doubles
+//   mailbox  [site 0..1][parity 0..1][src rank][4 x u64] = {stamp32 | 32 payload bits} x 4 (two doubles)   16 W words
 //   hflag    [parity 0..1][src rank]                                          2 W doubles
 //   p        [owned nodes | ghost nodes][2]   the search direction of the PCG lives HERE on the peer path, so that
 //            neighbours write their boundary entries straight into its ghost segment and the SpMV gathers from one
@@ -142,6 +142,7 @@ struct P2PDev {
     double stamp;          // stamp of the CURRENT iteration (epoch * 2^32 + it + 1)
     int parity;            // it & 1
     int *err;              // set to 1 when a wait times out
+    unsigned int stamp32;  // 32-bit stamp carried inside every mailbox word
 };
 __host__ __device__ inline int64_t p2p_mbox_off(int W, int site, int parity, int src) { return ((int64_t)(site * 2 + parity) * W + src) * 4; }
 __host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 16 * (int64_t)W + (int64_t)parity * W + src; }

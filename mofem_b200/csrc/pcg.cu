@@ -87,27 +87,46 @@ __device__ __forceinline__ bool p2p_wait(const volatile double *flag, double sta
     return true;
 }
 
-// all-reduce, producer side: called by ONE block after it holds this rank's partial(s)
+// All-reduce of one or two doubles in "LL" form (the trick NCCL's low-latency protocol uses): every 8-byte word carries
+// 32 bits of payload and a 32-bit stamp, and an aligned 8-byte store is atomic over NVLink -- so no fence and no
+// separate flag: one-way latency only.
+__device__ __forceinline__ unsigned int p2p_stamp32(const P2PDev &pp) { return pp.stamp32; }
+
+// producer side: called by ONE block after it holds this rank's partial(s)
 __device__ __forceinline__ void p2p_publish(const P2PDev &pp, int site, double v0, double v1)
 {
     if ((int)threadIdx.x < pp.world) {
-        double *slot = pp.peer[threadIdx.x] + p2p_mbox_off(pp.world, site, pp.parity, pp.rank);
-        slot[0] = v0; slot[1] = v1;
-        __threadfence_system();
-        *reinterpret_cast<volatile double *>(slot + 2) = pp.stamp;
+        volatile unsigned long long *slot =
+            reinterpret_cast<volatile unsigned long long *>(pp.peer[threadIdx.x] + p2p_mbox_off(pp.world, site, pp.parity, pp.rank));
+        const unsigned long long f = (unsigned long long)pp.stamp32 << 32;
+        const unsigned long long a = (unsigned long long)__double_as_longlong(v0), c = (unsigned long long)__double_as_longlong(v1);
+        slot[0] = f | (a & 0xffffffffull); slot[1] = f | (a >> 32);
+        slot[2] = f | (c & 0xffffffffull); slot[3] = f | (c >> 32);
     }
 }
 
-// all-reduce, consumer side: every block sums the W partials in rank order (bit-identical on every rank and block)
+// consumer side: every block sums the W partials in rank order (bit-identical on every rank and block)
 __device__ __forceinline__ void p2p_collect(const P2PDev &pp, int site, double &v0, double &v1)
 {
     __shared__ double sv[2][64];
     if ((int)threadIdx.x < pp.world) {
-        const double *slot = pp.local + p2p_mbox_off(pp.world, site, pp.parity, threadIdx.x);
-        p2p_wait(reinterpret_cast<const volatile double *>(slot + 2), pp.stamp, pp.err);
-        __threadfence_system();
-        sv[0][threadIdx.x] = *reinterpret_cast<const volatile double *>(slot);
-        sv[1][threadIdx.x] = *reinterpret_cast<const volatile double *>(slot + 1);
+        const volatile unsigned long long *slot =
+            reinterpret_cast<const volatile unsigned long long *>(pp.local + p2p_mbox_off(pp.world, site, pp.parity, threadIdx.x));
+        unsigned long long wv[4];
+        long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { wv[j] = slot[j]; ok = ok && (unsigned int)(wv[j] >> 32) == pp.stamp32; }
+            if (ok) break;
+            if ((spins & 0xfff) == 0xfff) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 40000000000ll) { *pp.err = 1; break; }
+            }
+        }
+        sv[0][threadIdx.x] = __longlong_as_double((long long)((wv[0] & 0xffffffffull) | (wv[1] << 32)));
+        sv[1][threadIdx.x] = __longlong_as_double((long long)((wv[2] & 0xffffffffull) | (wv[3] << 32)));
     }
     __syncthreads();
     double a = 0.0, c = 0.0;
@@ -451,7 +470,7 @@ static int spmv_grid(int64_t n_node)
     return (int)g;
 }
 
-static const P2PDev NO_P2P{nullptr, nullptr, 1, 0, 0.0, 0, nullptr};
+static const P2PDev NO_P2P{nullptr, nullptr, 1, 0, 0.0, 0, nullptr, 0u};
 
 // plain launch: ghosts (if any) are the tail of x
 template <bool DOT>
@@ -542,6 +561,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
         if (peer) {
             pp.peer = dist->peer; pp.local = dist->xbuf; pp.world = W; pp.rank = dist->rank;
             pp.stamp = stamp0 + (double)it_for + 1.0; pp.parity = it_for & 1; pp.err = err_dev;
+            pp.stamp32 = (unsigned int)(((dist->epoch & 0xfff) << 20) | (((int64_t)it_for + 1) & 0xfffff));
         }
         return pp;
     };
