@@ -156,6 +156,7 @@ struct PcgBuffers {
     double *x, *r, *p, *q, *dinv, *b, *ufix;  // n each
     double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
     double *sc;                                // 8 scalars
+    uint8_t *row_halo;                         // [local nodes] 1 = row references a ghost column (peer path)
     unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = peer time-out flag
 };
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,

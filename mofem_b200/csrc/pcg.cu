@@ -135,75 +135,114 @@ __device__ __forceinline__ void p2p_collect(const P2PDev &pp, int site, double &
     __syncthreads();
 }
 
-// y = K x on node rows; fixed rows -> 0.  Optionally the dot product x.y goes to *dot_out.
-// Ghost columns are the tail of x.
-// P2P: wait for the neighbours' halo stamps before touching ghosts; publish the dot-product partial to every peer.
+struct HaloPush {          // peer path: what a kernel needs to deliver this rank's boundary entries of p to the neighbours
+    int64_t n_send;
+    const int32_t *send_idx, *send_nb;
+    const int64_t *send_dst, *nb_ghost_off;
+    const int *nb_rank;
+    int n_nb;
+};
+
+// one node row (two scalar rows) by a group of SPMV_LANES lanes; the sums are valid in every lane of the group
+__device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__restrict__ node_ptr,
+                                         const int32_t *__restrict__ node_idx, const double *__restrict__ data,
+                                         const double *__restrict__ x, double &y0, double &y1)
+{
+    const int64_t r0 = node_ptr[a];
+    const int deg = (int)(node_ptr[a + 1] - r0);
+    const double2 *d0 = reinterpret_cast<const double2 *>(data + 4 * r0);
+    const double2 *d1 = reinterpret_cast<const double2 *>(data + 4 * r0 + 2 * deg);
+    for (int kb = sub; kb < deg; kb += SPMV_LANES * SPMV_UNROLL) {
+        double2 v0[SPMV_UNROLL], v1[SPMV_UNROLL], xv[SPMV_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SPMV_UNROLL; u++) {
+            const int kk = kb + u * SPMV_LANES;
+            if (kk < deg) {
+                const int c = __ldg(node_idx + r0 + kk);
+                v0[u] = __ldcs(d0 + kk);
+                v1[u] = __ldcs(d1 + kk);
+                xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
+            } else {
+                v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_UNROLL; u++) {
+            y0 = fma(v0[u].x, xv[u].x, y0); y0 = fma(v0[u].y, xv[u].y, y0);
+            y1 = fma(v1[u].x, xv[u].x, y1); y1 = fma(v1[u].y, xv[u].y, y1);
+        }
+    }
+}
+
+// y = K x on node rows; fixed rows -> 0.  Optionally the dot product x.y goes to *dot_out.  Ghost columns are the tail
+// of x.
+// P2P (row-partitioned, peer transport) -- one kernel does the halo exchange, the product and the all-reduce hand-off:
+//   * block 0 first writes this rank's boundary entries of x into the ghost segment of the neighbours' x over NVLink and
+//     raises its stamp there;
+//   * every block multiplies its rows that touch no ghost column, and only then waits for the neighbours' stamps and
+//     multiplies the few rows that do (row_halo) -- the NVLink latency hides behind the interior rows;
+//   * the last block publishes the dot-product partial into every peer's mailbox.
 template <bool DOT, bool P2P>
-__global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
+__global__ void __launch_bounds__(SPMV_BLOCK, P2P ? SPMV_MINB - 2 : SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
        const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
-       P2PDev pp, int n_wait, const int *__restrict__ wait_rank)
+       P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo, HaloPush hp)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
-    if (P2P) {
-        if ((int)threadIdx.x < n_wait) {
-            p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
-                     pp.stamp, pp.err);
-            __threadfence_system();
+    if (P2P && blockIdx.x == 0 && hp.n_nb) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        for (int64_t i = threadIdx.x; i < hp.n_send; i += blockDim.x) {
+            const int k = hp.send_nb[i];
+            double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
+            *dst = x2[hp.send_idx[i]];
         }
+        __threadfence_system();
         __syncthreads();
+        if ((int)threadIdx.x < hp.n_nb)
+            *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
     }
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
     double dot = 0.0;
-    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
-        const int64_t a = row0 + threadIdx.x / SPMV_LANES;
-        double y0 = 0.0, y1 = 0.0;
-        if (a < n_node) {
-            const int64_t r0 = node_ptr[a];
-            const int deg = (int)(node_ptr[a + 1] - r0);
-            const double2 *d0 = reinterpret_cast<const double2 *>(data + 4 * r0);
-            const double2 *d1 = reinterpret_cast<const double2 *>(data + 4 * r0 + 2 * deg);
-            for (int kb = sub; kb < deg; kb += SPMV_LANES * SPMV_UNROLL) {
-                double2 v0[SPMV_UNROLL], v1[SPMV_UNROLL], xv[SPMV_UNROLL];
-#pragma unroll
-                for (int u = 0; u < SPMV_UNROLL; u++) {
-                    const int kk = kb + u * SPMV_LANES;
-                    if (kk < deg) {
-                        const int c = __ldg(node_idx + r0 + kk);
-                        v0[u] = __ldcs(d0 + kk);
-                        v1[u] = __ldcs(d1 + kk);
-                        // peer path: the ghost segment of x is written by other GPUs before their stamp arrives; no block
-                        // reads it before its own wait below has passed and L1 starts empty at kernel launch, so the
-                        // cached read-only path is safe here too
-                        xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
-                    } else {
-                        v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < SPMV_UNROLL; u++) {
-                    y0 = fma(v0[u].x, xv[u].x, y0); y0 = fma(v0[u].y, xv[u].y, y0);
-                    y1 = fma(v1[u].x, xv[u].x, y1); y1 = fma(v1[u].y, xv[u].y, y1);
-                }
+    int deferred = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < (P2P ? 2 : 1); pass++) {
+        if (P2P && pass == 1) {
+            if (!__syncthreads_or(deferred)) break;        // this block has no row that touches a ghost column
+            if ((int)threadIdx.x < n_wait) {
+                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+                         pp.stamp, pp.err);
+                __threadfence_system();
             }
+            __syncthreads();
         }
-#pragma unroll
-        for (int d = SPMV_LANES / 2; d; d >>= 1) {
-            y0 += __shfl_xor_sync(0xffffffffu, y0, d);
-            y1 += __shfl_xor_sync(0xffffffffu, y1, d);
-        }
-        if (a < n_node && sub == 0) {
-            if (fixed) {
-                const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
-                if (fx.x) y0 = 0.0;
-                if (fx.y) y1 = 0.0;
+        for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
+            const int64_t a = row0 + threadIdx.x / SPMV_LANES;
+            bool mine = a < n_node;
+            if (P2P && mine) {
+                const bool halo_row = row_halo[a] != 0;
+                if (pass == 0 && halo_row) deferred = 1;
+                mine = (pass == 1) == halo_row;
             }
-            *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
-            if (DOT) {
-                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
-                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+            double y0 = 0.0, y1 = 0.0;
+            if (mine) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+#pragma unroll
+            for (int d = SPMV_LANES / 2; d; d >>= 1) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+            }
+            if (mine && sub == 0) {
+                if (fixed) {
+                    const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
+                    if (fx.x) y0 = 0.0;
+                    if (fx.y) y1 = 0.0;
+                }
+                *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+                if (DOT) {
+                    const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                    dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+                }
             }
         }
     }
@@ -215,6 +254,17 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
             else if (threadIdx.x == 0) *dot_out = total;
         }
     }
+}
+
+// rows of the local matrix that reference a ghost column (peer path: they are multiplied after the halo has arrived)
+__global__ void k_mark_halo_rows(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
+                                 uint8_t *__restrict__ row_halo)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_node) return;
+    uint8_t h = 0;
+    for (int64_t k = node_ptr[a]; k < node_ptr[a + 1]; k++) h |= (node_idx[k] >= n_node);
+    row_halo[a] = h;
 }
 
 // diagonal -> inverse (0 on fixed or empty rows)
@@ -329,21 +379,10 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
 }
 
 // p = dinv*r + beta p      (beta = rz_new / rz_old)
-struct HaloPush {          // peer path: what the direction kernel needs to deliver the new p to the neighbours
-    int64_t n_send;
-    const int32_t *send_idx, *send_nb;
-    const int64_t *send_dst, *nb_ghost_off;
-    const int *nb_rank;
-    int n_nb;
-    unsigned int *counter;
-    double stamp_next;     // stamp / parity of iteration it + 1
-    int parity_next;
-};
-
 template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
-                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, HaloPush hp)
+                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp)
 {
     double rz_new, rr;
     if (P2P) {
@@ -359,28 +398,6 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
         double2 pi = p[i];
         pi.x = fma(beta, pi.x, di.x * ri.x); pi.y = fma(beta, pi.y, di.y * ri.y);
         p[i] = pi;
-    }
-    if (P2P && hp.n_nb) {
-        // the last block to finish knows p is complete: it writes this rank's boundary entries into the ghost segment of
-        // the neighbours' p over NVLink and then raises its flag there (fused compute + halo exchange, no extra launch)
-        __shared__ bool last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) last = (atomicAdd(hp.counter, 1u) == gridDim.x - 1);
-        __syncthreads();
-        if (last) {
-            __threadfence();
-            for (int64_t i = threadIdx.x; i < hp.n_send; i += blockDim.x) {
-                const int k = hp.send_nb[i];
-                double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
-                *dst = __ldcg(p + hp.send_idx[i]);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if ((int)threadIdx.x < hp.n_nb)
-                *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, hp.parity_next, pp.rank)) = hp.stamp_next;
-            if (threadIdx.x == 0) *hp.counter = 0u;
-        }
     }
 }
 
@@ -479,7 +496,7 @@ static void launch_spmv(const DevSystem &A, const double *x, double *y, const ui
 {
     const int64_t n_node = A.n_own / 2;
     k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
-                                                                 dot_out, NO_P2P, 0, nullptr);
+                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, HaloPush{});
 }
 
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
@@ -551,6 +568,8 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     if (peer) {   // the search direction lives in the exchange buffer (neighbours write its ghost segment)
         w.p = dist->xbuf + p2p_p_off(dist->world);
         p2 = reinterpret_cast<double2 *>(w.p);
+        if (n_node) k_mark_halo_rows<<<(unsigned)((n_node + 255) / 256), 256, 0, s>>>(n_node, A.node_ptr, A.node_idx, w.row_halo);
+        if (launches) ++*launches;
     }
     const int W = dist ? dist->world : 1;
     DistPlan *dm = const_cast<DistPlan *>(dist);
@@ -619,25 +638,26 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                                                             w.counters + 1, NO_P2P);
                 if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, HaloPush{});
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             } else {
                 const P2PDev pp = ppdev(it);
-                if (fresh) {   // halo of a freshly initialised p: NCCL, nothing to wait for
+                HaloPush hp{};
+                if (fresh) {   // halo of a freshly initialised p: NCCL, nothing to push or to wait for
                     if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
+                } else {
+                    hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
+                    hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb;
                 }
                 k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
-                                                            w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank);
+                                                            w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank,
+                                                            w.row_halo, hp);
                 fresh = false;
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
                                                            w.counters + 1, pp);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                HaloPush hp{};
-                hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
-                hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb; hp.counter = w.counters + 4;
-                hp.stamp_next = stamp0 + (double)(it + 1) + 1.0; hp.parity_next = (it + 1) & 1;
-                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp, hp);
+                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             }
         }
