@@ -35,6 +35,7 @@ struct mofem_ctx {
     int64_t sys_n = 0;
     double *slab = nullptr;
     size_t slab_hot_bytes = 0;
+    bool slab_in_xbuf = false;
     int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -437,14 +438,21 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
     cudaStream_t s = ctx->stream;
     const int64_t n = 2 * ctx->P.n_node;
     int rc;
-    if (ctx->sys_n != n || ctx->sys_allocs.empty()) {
+    const bool want_xbuf = ctx->have_halo && ctx->dist.p2p;
+    if (ctx->sys_n != n || ctx->sys_allocs.empty() || want_xbuf != ctx->slab_in_xbuf) {
         free_pool(ctx, ctx->sys_allocs);
         auto &pool = ctx->sys_allocs;
         PcgBuffers &W = ctx->W;
-        // the five vectors the PCG loop touches every iteration live in one slab (the L2 persistence window of mofem_solve)
-        const int64_t npad = (n + 31) & ~(int64_t)31;
+        // the five vectors the PCG loop touches every iteration live in one slab (the L2 persistence window of mofem_solve);
+        // on the peer path the slab is part of the IPC-exported exchange buffer
+        const int64_t npad = p2p_slab_pad(n);
         double *slab;
-        if ((rc = dev_alloc(ctx, &slab, 7 * npad, pool))) return rc;
+        if (want_xbuf) {
+            if (n != 2 * (ctx->dist.n_owned_node + ctx->dist.n_ghost))
+                return ctx_fail(ctx, MOFEM_E_ARG, "mofem_set_system: problem size does not match the halo plan of the peer transport");
+            slab = ctx->dist.xbuf + p2p_p_off(ctx->dist.world);
+        } else if ((rc = dev_alloc(ctx, &slab, 7 * npad, pool))) return rc;
+        ctx->slab_in_xbuf = want_xbuf;
         W.p = slab; W.q = slab + npad; W.x = slab + 2 * npad; W.r = slab + 3 * npad; W.dinv = slab + 4 * npad;
         W.b = slab + 5 * npad; W.ufix = slab + 6 * npad;
         ctx->slab = slab; ctx->slab_hot_bytes = sizeof(double) * (size_t)(5 * npad);
@@ -636,6 +644,11 @@ static void p2p_close(mofem_ctx *ctx)
 {
     DistPlan &D = ctx->dist;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->slab_in_xbuf) {   // the PCG vectors lived in the exchange buffer: the system has to be set again
+        free_pool(ctx, ctx->sys_allocs);
+        ctx->sys_n = 0; ctx->slab_in_xbuf = false; ctx->slab = nullptr; ctx->slab_hot_bytes = 0;
+        ctx->have_system = ctx->have_solution = false;
+    }
     for (int r = 0; r < (int)D.peer_host.size(); r++)
         if (r != D.rank && D.peer_host[r]) cudaIpcCloseMemHandle(D.peer_host[r]);
     D.peer_host.clear();

@@ -132,9 +132,9 @@ struct DistPlan {
 // Exchange-buffer layout (doubles), identical on every rank (world = W):
 //   mailbox  [site 0..1][parity 0..1][src rank][4 x u64] = {stamp32 | 32 payload bits} x 4 (two doubles)   16 W words
 //   hflag    [parity 0..1][src rank]                                          2 W doubles
-//   p        [owned nodes | ghost nodes][2]   the search direction of the PCG lives HERE on the peer path, so that
-//            neighbours write their boundary entries straight into its ghost segment and the SpMV gathers from one
-//            contiguous vector
+//   slab     p, q, x, r, dinv, b, ufix -- the PCG vectors live HERE on the peer path (p first: [owned | ghost nodes][2]),
+//            so that neighbours write their boundary entries straight into the ghost segment of p and the SpMV gathers
+//            from one contiguous vector
 struct P2PDev {
     double *const *peer;   // device array [world]
     double *local;         // == peer[rank]
@@ -147,7 +147,9 @@ struct P2PDev {
 __host__ __device__ inline int64_t p2p_mbox_off(int W, int site, int parity, int src) { return ((int64_t)(site * 2 + parity) * W + src) * 4; }
 __host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 16 * (int64_t)W + (int64_t)parity * W + src; }
 __host__ __device__ inline int64_t p2p_p_off(int W) { return 18 * (int64_t)W; }
-inline int64_t p2p_buffer_doubles(int W, int64_t n_local_node) { return 18 * (int64_t)W + 2 * n_local_node + 8; }
+inline int64_t p2p_slab_pad(int64_t n_local_dof) { return (n_local_dof + 31) & ~(int64_t)31; }
+// mailboxes + flags + the whole PCG vector slab (p first): one allocation, one L2 persistence window
+inline int64_t p2p_buffer_doubles(int W, int64_t n_local_node) { return 18 * (int64_t)W + 7 * p2p_slab_pad(2 * n_local_node) + 8; }
 
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
 

@@ -179,11 +179,11 @@ __device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__re
 // P2P (row-partitioned, peer transport) -- one kernel does the halo exchange, the product and the all-reduce hand-off:
 //   * block 0 first writes this rank's boundary entries of x into the ghost segment of the neighbours' x over NVLink and
 //     raises its stamp there;
-//   * every block multiplies its rows that touch no ghost column, and only then waits for the neighbours' stamps and
-//     multiplies the few rows that do (row_halo) -- the NVLink latency hides behind the interior rows;
+//   * rows that touch no ghost column are multiplied straight away; the few that do (row_halo) make their lane group wait
+//     for the neighbours' stamps first -- the NVLink latency hides behind the interior rows;
 //   * the last block publishes the dot-product partial into every peer's mailbox.
 template <bool DOT, bool P2P>
-__global__ void __launch_bounds__(SPMV_BLOCK, P2P ? SPMV_MINB - 2 : SPMV_MINB)
+__global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
        const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
@@ -205,44 +205,33 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
     double dot = 0.0;
-    int deferred = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < (P2P ? 2 : 1); pass++) {
-        if (P2P && pass == 1) {
-            if (!__syncthreads_or(deferred)) break;        // this block has no row that touches a ghost column
-            if ((int)threadIdx.x < n_wait) {
-                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
+        const int64_t a = row0 + threadIdx.x / SPMV_LANES;
+        if (P2P && a < n_node && row_halo[a]) {
+            // this row gathers ghost entries: its lane group waits here for the neighbours' stamps.  Only the few
+            // groups that own such rows ever wait; everybody else streams on, hiding the NVLink latency.
+            for (int k = 0; k < n_wait; k++)
+                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[k])),
                          pp.stamp, pp.err);
-                __threadfence_system();
-            }
-            __syncthreads();
+            __threadfence();
         }
-        for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
-            const int64_t a = row0 + threadIdx.x / SPMV_LANES;
-            bool mine = a < n_node;
-            if (P2P && mine) {
-                const bool halo_row = row_halo[a] != 0;
-                if (pass == 0 && halo_row) deferred = 1;
-                mine = (pass == 1) == halo_row;
-            }
-            double y0 = 0.0, y1 = 0.0;
-            if (mine) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+        double y0 = 0.0, y1 = 0.0;
+        if (a < n_node) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
 #pragma unroll
-            for (int d = SPMV_LANES / 2; d; d >>= 1) {
-                y0 += __shfl_xor_sync(0xffffffffu, y0, d);
-                y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+        for (int d = SPMV_LANES / 2; d; d >>= 1) {
+            y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+            y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+        }
+        if (a < n_node && sub == 0) {
+            if (fixed) {
+                const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
+                if (fx.x) y0 = 0.0;
+                if (fx.y) y1 = 0.0;
             }
-            if (mine && sub == 0) {
-                if (fixed) {
-                    const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
-                    if (fx.x) y0 = 0.0;
-                    if (fx.y) y1 = 0.0;
-                }
-                *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
-                if (DOT) {
-                    const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
-                    dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
-                }
+            *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+            if (DOT) {
+                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
             }
         }
     }
@@ -556,7 +545,7 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, const DistPlan *dist, double rtol, int maxit,
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
 {
-    PcgBuffers w = w_in;   // local copy: the peer path redirects p into the exchange buffer
+    PcgBuffers &w = w_in;
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
     const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
@@ -565,9 +554,8 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     double2 *x2 = reinterpret_cast<double2 *>(w.x), *r2 = reinterpret_cast<double2 *>(w.r);
     double2 *p2 = reinterpret_cast<double2 *>(w.p), *q2 = reinterpret_cast<double2 *>(w.q);
     const bool peer = dist && dist->p2p && dist->world > 1;
-    if (peer) {   // the search direction lives in the exchange buffer (neighbours write its ghost segment)
-        w.p = dist->xbuf + p2p_p_off(dist->world);
-        p2 = reinterpret_cast<double2 *>(w.p);
+    if (peer) {   // the vector slab lives in the exchange buffer (mofem_set_system): neighbours write the ghost segment of p
+        if (w.p != dist->xbuf + p2p_p_off(dist->world)) return cudaErrorInvalidValue;
         if (n_node) k_mark_halo_rows<<<(unsigned)((n_node + 255) / 256), 256, 0, s>>>(n_node, A.node_ptr, A.node_idx, w.row_halo);
         if (launches) ++*launches;
     }
