@@ -338,6 +338,9 @@ def main():
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
+    if prof["iterations"]:
+        log(f"[rank {rank}] per-iteration us: spmv {prof['spmv_ms'] / prof['iterations'] * 1e3:.1f} "
+            f"update {prof['update_ms'] / prof['iterations'] * 1e3:.1f} direction {prof['direction_ms'] / prof['iterations'] * 1e3:.1f}")
     step_ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
         t = torch.tensor([step_ms], dtype=torch.float64, device=dev)

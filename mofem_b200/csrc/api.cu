@@ -659,6 +659,8 @@ static void p2p_close(mofem_ctx *ctx)
     if (D.nb_ghost_off) cudaFree(D.nb_ghost_off);
     if (D.nb_rank_dev) cudaFree(D.nb_rank_dev);
     if (D.wait_rank) cudaFree(D.wait_rank);
+    if (D.halo_rows) cudaFree(D.halo_rows);
+    D.halo_rows = nullptr; D.n_halo_rows = 0; D.halo_rows_cap = 0;
     D.xbuf = nullptr; D.peer = nullptr; D.send_nb = nullptr; D.send_dst = nullptr; D.nb_ghost_off = nullptr;
     D.nb_rank_dev = nullptr; D.wait_rank = nullptr; D.n_wait = 0;
     D.p2p = false;

@@ -127,6 +127,8 @@ struct DistPlan {
     int *wait_rank = nullptr;                  // device [n_wait]: ranks this rank receives ghosts from
     int n_wait = 0;
     int64_t epoch = 0;                         // solves done on the peer path (stamps are unique per solve)
+    int32_t *halo_rows = nullptr;              // device: owned rows that reference a ghost column (rebuilt per solve)
+    int64_t n_halo_rows = 0, halo_rows_cap = 0;
 };
 
 // Exchange-buffer layout (doubles), identical on every rank (world = W):

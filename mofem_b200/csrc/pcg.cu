@@ -179,15 +179,16 @@ __device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__re
 // P2P (row-partitioned, peer transport) -- one kernel does the halo exchange, the product and the all-reduce hand-off:
 //   * block 0 first writes this rank's boundary entries of x into the ghost segment of the neighbours' x over NVLink and
 //     raises its stamp there;
-//   * rows that touch no ghost column are multiplied straight away; the few that do (row_halo) make their lane group wait
-//     for the neighbours' stamps first -- the NVLink latency hides behind the interior rows;
+//   * every block first multiplies its rows that touch no ghost column; the few that do (halo_rows) are dealt out afterwards,
+//     behind a wait for the neighbours' stamps -- the NVLink latency hides behind the interior rows;
 //   * the last block publishes the dot-product partial into every peer's mailbox.
 template <bool DOT, bool P2P>
 __global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
        const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
-       P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo, HaloPush hp)
+       P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo,
+       const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
     if (P2P && blockIdx.x == 0 && hp.n_nb) {
@@ -205,24 +206,13 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
     double dot = 0.0;
-    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
-        const int64_t a = row0 + threadIdx.x / SPMV_LANES;
-        if (P2P && a < n_node && row_halo[a]) {
-            // this row gathers ghost entries: its lane group waits here for the neighbours' stamps.  Only the few
-            // groups that own such rows ever wait; everybody else streams on, hiding the NVLink latency.
-            for (int k = 0; k < n_wait; k++)
-                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[k])),
-                         pp.stamp, pp.err);
-            __threadfence();
-        }
-        double y0 = 0.0, y1 = 0.0;
-        if (a < n_node) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+    auto finish_row = [&](int64_t a, double y0, double y1) {
 #pragma unroll
         for (int d = SPMV_LANES / 2; d; d >>= 1) {
             y0 += __shfl_xor_sync(0xffffffffu, y0, d);
             y1 += __shfl_xor_sync(0xffffffffu, y1, d);
         }
-        if (a < n_node && sub == 0) {
+        if (a >= 0 && sub == 0) {
             if (fixed) {
                 const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
                 if (fx.x) y0 = 0.0;
@@ -232,6 +222,32 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
             if (DOT) {
                 const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
                 dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+            }
+        }
+    };
+    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
+        int64_t a = row0 + threadIdx.x / SPMV_LANES;
+        if (a >= n_node || (P2P && row_halo[a])) a = -1;        // halo rows come last (below)
+        double y0 = 0.0, y1 = 0.0;
+        if (a >= 0) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+        finish_row(a, y0, y1);
+    }
+    if (P2P) {
+        // rows that gather ghost entries: a compact list, dealt block by block AFTER the interior rows, behind a wait for
+        // the neighbours' stamps -- by then the halo has long arrived and the NVLink latency is hidden
+        const int64_t h0 = (int64_t)blockIdx.x * rows_per_block;
+        if (h0 < n_halo) {
+            if ((int)threadIdx.x < n_wait)
+                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+                         pp.stamp, pp.err);
+            __syncthreads();
+            __threadfence();
+            for (int64_t i0 = h0; i0 < n_halo; i0 += (int64_t)gridDim.x * rows_per_block) {
+                const int64_t i = i0 + threadIdx.x / SPMV_LANES;
+                const int64_t a = i < n_halo ? halo_rows[i] : -1;
+                double y0 = 0.0, y1 = 0.0;
+                if (a >= 0) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+                finish_row(a, y0, y1);
             }
         }
     }
@@ -485,7 +501,7 @@ static void launch_spmv(const DevSystem &A, const double *x, double *y, const ui
 {
     const int64_t n_node = A.n_own / 2;
     k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
-                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, HaloPush{});
+                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, nullptr, 0, HaloPush{});
 }
 
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
@@ -556,8 +572,24 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     const bool peer = dist && dist->p2p && dist->world > 1;
     if (peer) {   // the vector slab lives in the exchange buffer (mofem_set_system): neighbours write the ghost segment of p
         if (w.p != dist->xbuf + p2p_p_off(dist->world)) return cudaErrorInvalidValue;
+        // which rows gather ghost entries: marked on the device, compacted on the host (once per solve; a few thousand rows)
         if (n_node) k_mark_halo_rows<<<(unsigned)((n_node + 255) / 256), 256, 0, s>>>(n_node, A.node_ptr, A.node_idx, w.row_halo);
         if (launches) ++*launches;
+        std::vector<uint8_t> mark((size_t)n_node);
+        if ((e = cudaMemcpyAsync(mark.data(), w.row_halo, (size_t)n_node, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        std::vector<int32_t> rows;
+        for (int64_t a = 0; a < n_node; a++) if (mark[a]) rows.push_back((int32_t)a);
+        DistPlan *dmut = const_cast<DistPlan *>(dist);
+        if ((int64_t)rows.size() > dmut->halo_rows_cap) {
+            if (dmut->halo_rows) cudaFree(dmut->halo_rows);
+            dmut->halo_rows_cap = (int64_t)rows.size() + 1024;
+            if ((e = cudaMalloc(&dmut->halo_rows, sizeof(int32_t) * dmut->halo_rows_cap)) != cudaSuccess) return e;
+        }
+        dmut->n_halo_rows = (int64_t)rows.size();
+        if (!rows.empty() &&
+            (e = cudaMemcpyAsync(dmut->halo_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     }
     const int W = dist ? dist->world : 1;
     DistPlan *dm = const_cast<DistPlan *>(dist);
@@ -639,7 +671,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                 }
                 k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
                                                             w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank,
-                                                            w.row_halo, hp);
+                                                            w.row_halo, dist->halo_rows, dist->n_halo_rows, hp);
                 fresh = false;
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
