@@ -50,7 +50,7 @@ struct mofem_ctx {
     std::vector<cudaEvent_t> prof_events;
     double prof_ms[4]{};
 };
-constexpr int PCG_CHUNK = 50;
+constexpr int PCG_CHUNK = 250;   // iterations enqueued between host polls (the device stops early on its own)
 
 static int ctx_fail(mofem_ctx *ctx, int code, const std::string &msg)
 {
@@ -458,7 +458,7 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
         ctx->slab = slab; ctx->slab_hot_bytes = sizeof(double) * (size_t)(5 * npad);
         if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
-            (rc = dev_alloc(ctx, &W.sc, 8, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+            (rc = dev_alloc(ctx, &W.sc, 16, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;

@@ -28,7 +28,11 @@ static_assert(SPMV_GRID_CAP <= PCG_MAX_PART, "partials buffer too small");
 
 // scalar slots in PcgBuffers::sc: (rz, rr) pairs double-buffered by iteration parity at [0,1] and [2,3] -- each pair
 // is contiguous so that the row-partitioned solve all-reduces it in one call.
-enum { SC_BNORM2 = 4, SC_RR_TRUE = 5, SC_ENERGY = 6, SC_PQ = 7 };
+enum { SC_BNORM2 = 4, SC_RR_TRUE = 5, SC_ENERGY = 6, SC_PQ = 7, SC_DONE = 8, SC_IT_DONE = 9, SC_PART_RZ = 10, SC_PART_PQ = 12, SC_COUNT = 16 };
+// SC_PART_*: per-rank partials on the NCCL path (all-reduced INTO the global slots, so that re-reducing after the device
+// has stopped is idempotent).
+// SC_DONE: set by the direction kernel of the iteration whose recurrence residual met the tolerance; every later kernel
+// of the chunk returns at once, so the host can poll rarely (large chunks) without paying for overshoot iterations.
 __host__ __device__ inline int sc_rz(int it) { return 2 * (it & 1); }
 __host__ __device__ inline int sc_rr(int it) { return 2 * (it & 1) + 1; }
 
@@ -188,9 +192,10 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
        const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
        P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo,
-       const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp)
+       const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp, const double *done_flag)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
+    if (DOT && done_flag && *done_flag != 0.0) return;
     if (P2P && blockIdx.x == 0 && hp.n_nb) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         for (int64_t i = threadIdx.x; i < hp.n_send; i += blockDim.x) {
@@ -347,6 +352,7 @@ k_pcg_init(int64_t n2, const double2 *__restrict__ b, const double2 *__restrict_
 __global__ void k_pcg_init_finish(double *__restrict__ sc, int keep_x)
 {
     sc[2] = sc[0]; sc[3] = sc[1];
+    sc[SC_DONE] = 0.0; sc[SC_IT_DONE] = 0.0;
     if (!keep_x) sc[SC_BNORM2] = sc[1];
 }
 
@@ -355,9 +361,10 @@ template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ p, const double2 *__restrict__ q,
              const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r,
-             double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp)
+             double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp, double *out2)
 {
     __shared__ double sm[VEC_BLOCK / 32];
+    if (sc[SC_DONE] != 0.0) return;
     double pq, unused;
     if (P2P) p2p_collect(pp, 0, pq, unused);
     else pq = sc[SC_PQ];
@@ -379,7 +386,7 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
     double a, c;
     if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c)) {
         if (P2P) p2p_publish(pp, 1, a, c);
-        else if (threadIdx.x == 0) { sc[sc_rz(it + 1)] = a; sc[sc_rr(it + 1)] = c; }
+        else if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
     }
 }
 
@@ -387,14 +394,27 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
 template <bool P2P>
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
-                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp)
+                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, double tol2, unsigned int *done_counter)
 {
+    if (sc[SC_DONE] != 0.0) return;
     double rz_new, rr;
     if (P2P) {
         p2p_collect(pp, 1, rz_new, rr);
         if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr; }   // for the host poll
     } else {
         rz_new = sc[sc_rz(it + 1)];
+        rr = sc[sc_rr(it + 1)];
+    }
+    if (rr <= tol2) {
+        // converged by the recurrence residual: the LAST block to get here raises the flag (the others may still be reading
+        // it at their entry), so the remaining kernels of the chunk become no-ops; p is left as it is
+        __shared__ bool last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+            if (last) { sc[SC_IT_DONE] = (double)(it + 1); sc[SC_DONE] = 1.0; *done_counter = 0u; }
+        }
+        return;
     }
     const double rz_old = sc[sc_rz(it)];
     const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
@@ -463,12 +483,12 @@ static cudaError_t halo_exchange(const DistPlan *d, const double *v, double *gho
     return cudaGetLastError();
 }
 
-static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStream_t s)
+static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStream_t s, const double *src = nullptr)
 {
     if (!d || d->world <= 1) return cudaSuccess;
     const NcclApi *nc = nccl_api();
     if (!nc) return cudaErrorUnknown;
-    NCCL_OK(nc->AllReduce(v, v, (size_t)count, ncclDouble, ncclSum, d->comm, s));
+    NCCL_OK(nc->AllReduce(src ? src : v, v, (size_t)count, ncclDouble, ncclSum, d->comm, s));
     return cudaSuccess;
 }
 
@@ -497,11 +517,11 @@ static const P2PDev NO_P2P{nullptr, nullptr, 1, 0, 0.0, 0, nullptr, 0u};
 // plain launch: ghosts (if any) are the tail of x
 template <bool DOT>
 static void launch_spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, double *part, unsigned int *counter,
-                        double *dot_out, cudaStream_t s)
+                        double *dot_out, cudaStream_t s, const double *done = nullptr)
 {
     const int64_t n_node = A.n_own / 2;
     k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
-                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, nullptr, 0, HaloPush{});
+                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, nullptr, 0, HaloPush{}, done);
 }
 
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
@@ -565,7 +585,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
     const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
-    double sc_host[10];
+    double sc_host[SC_COUNT];
     const double2 *b2 = reinterpret_cast<const double2 *>(w.b), *dinv2 = reinterpret_cast<const double2 *>(w.dinv);
     double2 *x2 = reinterpret_cast<double2 *>(w.x), *r2 = reinterpret_cast<double2 *>(w.r);
     double2 *p2 = reinterpret_cast<double2 *>(w.p), *q2 = reinterpret_cast<double2 *>(w.q);
@@ -613,7 +633,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
         return cudaGetLastError();
     };
     if ((e = init(0)) != cudaSuccess) return e;
-    e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, s);
+    e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return e;
@@ -651,14 +671,15 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
             if (ev) cudaEventRecord(ev[4 * k], s);
             if (!peer) {
                 if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
-                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + SC_PQ, s);
-                if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s)) != cudaSuccess) return done(e);
+                const bool multi = dist && dist->world > 1;   // NCCL: partials are all-reduced INTO the global slots
+                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + (multi ? SC_PART_PQ : SC_PQ), s, w.sc + SC_DONE);
+                if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s, w.sc + SC_PART_PQ)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
-                                                            w.counters + 1, NO_P2P);
-                if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s)) != cudaSuccess) return done(e);
+                                                            w.counters + 1, NO_P2P, w.sc + (multi ? SC_PART_RZ : sc_rz(it + 1)));
+                if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s, w.sc + SC_PART_RZ)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P);
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, tol2, w.counters + 5);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             } else {
                 const P2PDev pp = ppdev(it);
@@ -671,19 +692,19 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                 }
                 k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
                                                             w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank,
-                                                            w.row_halo, dist->halo_rows, dist->n_halo_rows, hp);
+                                                            w.row_halo, dist->halo_rows, dist->n_halo_rows, hp, w.sc + SC_DONE);
                 fresh = false;
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
-                                                           w.counters + 1, pp);
+                                                           w.counters + 1, pp, nullptr);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp);
+                k_pcg_direction<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, pp, tol2, w.counters + 5);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             }
         }
         if (launches) *launches += 3 * (int64_t)todo;
         harvest();  // events of the previous chunk, while this one runs
-        e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, s);
+        e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
         int err_host = 0;
         if (peer) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -692,6 +713,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
         if (e != cudaSuccess) return done(e);
         if (err_host) return done(cudaErrorLaunchTimeout);   // a peer did not answer within 10 s
         if (prof) { pend_pool = pool; pend_n = todo; pool ^= 1; }
+        if (sc_host[SC_DONE] != 0.0) it = (int)sc_host[SC_IT_DONE];   // the device stopped early inside the chunk
         info->iterations = it;
         const double rr = sc_host[sc_rr(it)];
         info->relres_rec = sqrt(rr / bnorm2);
