@@ -364,7 +364,9 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
              double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp, double *out2)
 {
     __shared__ double sm[VEC_BLOCK / 32];
-    if (sc[SC_DONE] != 0.0) return;
+    if (out2 == nullptr || out2 != sc + sc_rz(it + 1)) {   // row-partitioned runs poll rarely and rely on the stop flag
+        if (sc[SC_DONE] != 0.0) return;
+    }
     double pq, unused;
     if (P2P) p2p_collect(pp, 0, pq, unused);
     else pq = sc[SC_PQ];
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
                 const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, double tol2, unsigned int *done_counter)
 {
-    if (sc[SC_DONE] != 0.0) return;
+    if (done_counter && sc[SC_DONE] != 0.0) return;
     double rz_new, rr;
     if (P2P) {
         p2p_collect(pp, 1, rz_new, rr);
@@ -405,7 +407,7 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
         rz_new = sc[sc_rz(it + 1)];
         rr = sc[sc_rr(it + 1)];
     }
-    if (rr <= tol2) {
+    if (done_counter && rr <= tol2) {
         // converged by the recurrence residual: the LAST block to get here raises the flag (the others may still be reading
         // it at their entry), so the remaining kernels of the chunk become no-ops; p is left as it is
         __shared__ bool last;
@@ -663,6 +665,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     auto done = [&](cudaError_t ee) { harvest(); return ee; };
     const int n_nb = dist ? (int)dist->nb_rank.size() : 0;
     const int64_t n_send = dist && !dist->send_ptr.empty() ? dist->send_ptr.back() : 0;
+    if (!(dist && dist->world > 1) && chunk > 50) chunk = 50;   // a single GPU polls cheaply: no stop flag, short chunks
     while (it < maxit) {
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
@@ -672,14 +675,15 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
             if (!peer) {
                 if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
                 const bool multi = dist && dist->world > 1;   // NCCL: partials are all-reduced INTO the global slots
-                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + (multi ? SC_PART_PQ : SC_PQ), s, w.sc + SC_DONE);
+                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + (multi ? SC_PART_PQ : SC_PQ), s,
+                                  multi ? w.sc + SC_DONE : nullptr);
                 if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s, w.sc + SC_PART_PQ)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
                 k_pcg_update<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
                                                             w.counters + 1, NO_P2P, w.sc + (multi ? SC_PART_RZ : sc_rz(it + 1)));
                 if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s, w.sc + SC_PART_RZ)) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
-                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, tol2, w.counters + 5);
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, tol2, multi ? w.counters + 5 : nullptr);
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             } else {
                 const P2PDev pp = ppdev(it);
