@@ -9,6 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 NX, NY, WORLD = 16, 32, 2
+NY4 = 64          # 4-rank variant: middle ranks have two neighbours
 
 
 def _free_port():
@@ -19,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out, transport):
+def _worker(rank, world, port, out, transport, ny=NY):
     import torch
     import torch.distributed as dist
     from mofem_b200 import overlay_gen
@@ -32,9 +33,9 @@ def _worker(rank, world, port, out, transport):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        per = NY // 8 // world
-        strip, rhs, fixed, val = overlay_gen.patch_family(NX, ny=NY, patch_rows=(rank * per, (rank + 1) * per))
-        owner = _owner(strip, world)
+        per = ny // 8 // world
+        strip, rhs, fixed, val = overlay_gen.patch_family(NX, ny=ny, patch_rows=(rank * per, (rank + 1) * per))
+        owner = _owner(strip, world, ny=ny)
         part = exchange_send_lists(partition_problem(strip, owner, rank, world))
         with Context(rank) as ctx:
             init_comm(ctx)
@@ -73,6 +74,30 @@ def test_two_gpu_solve_matches_single_gpu(gpu_ctx, transport):
     assert np.array_equal(res[0][0], res[1][0])
     # same Krylov process: iteration counts agree to within one polling chunk
     assert abs(res[0][1]["iterations"] - info1["iterations"]) <= 50
+
+
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
+def test_four_gpu_solve_matches_single_gpu(gpu_ctx, transport):
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    import torch.multiprocessing as mp
+    from mofem_b200 import overlay_gen
+    fp, rhs, fixed, val = overlay_gen.patch_family(NX, ny=NY4)
+    gpu_ctx.clear_halo()
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    gpu_ctx.set_system(rhs, fixed, val)
+    u1, info1 = gpu_ctx.solve(rtol=1e-12)
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(4, port, out, transport, NY4), nprocs=4, join=True)
+        res = [out[r] for r in range(4)]
+    for u, info, energy in res:
+        assert info["converged"] == 1
+        assert np.abs(u - u1).max() <= 1e-9 * np.abs(u1).max()
+    for r in range(1, 4):
+        assert np.array_equal(res[0][0], res[r][0])
 
 
 def test_halo_plan_with_no_neighbours_is_the_single_gpu_path(gpu_ctx):
