@@ -16,7 +16,6 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 SOURCES = {
     "integrate.cu": ["-fmad=false"],
-    "fastquad.cu": ["-fmad=false"],
     "csr.cu": [],
     "scan.cu": [],
     "pcg.cu": [],

@@ -37,6 +37,7 @@ struct mofem_ctx {
     size_t slab_hot_bytes = 0;
     bool slab_in_xbuf = false;
     int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
+    int cell_kernel = 1;  // quad4 overlay cells on the warp-cooperative cell kernel (0: thread-per-block kernels only)
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms[6]{};
@@ -253,7 +254,7 @@ int mofem_symbolic(mofem_ctx *ctx)
         (rc = dev_alloc(ctx, &T.e2, T.n_task, pool)) || (rc = dev_alloc(ctx, &T.slots, T.n_task, pool)) ||
         (rc = dev_alloc(ctx, &T.cls, T.n_task, pool)) || (rc = dev_alloc(ctx, &T.pair_off, T.n_task, pool)) ||
         (rc = dev_alloc(ctx, &ctx->cls_tasks, T.n_task, pool))) { cleanup(); return rc; }
-    CKT(launch_fill_tasks(P, task_off, pair_off, T, s)); L++;
+    CKT(launch_fill_tasks(P, task_off, pair_off, T, ctx->cell_kernel, s)); L++;
     // class buckets
     int64_t *cls_count_d, *cls_start_d;
     if ((rc = dev_alloc(ctx, &cls_count_d, N_BUCKET, tmp)) || (rc = dev_alloc(ctx, &cls_start_d, N_BUCKET, tmp))) { cleanup(); return rc; }
@@ -320,7 +321,7 @@ int mofem_assemble(mofem_ctx *ctx)
     tic(ctx);
     for (int k = 0; k < N_CLASS; k++) {
         int64_t n_cls = 0;
-        for (int b = 0; b < N_SUB; b++) n_cls += ctx->cls_count[k * N_SUB + b];
+        for (int b = 0; b < (k == FAST_CLASS ? 1 : N_SUB); b++) n_cls += ctx->cls_count[k * N_SUB + b];   // FAST: first tasks only
         if (!n_cls) continue;
         CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB], n_cls, ctx->blk_val,
                                   ctx->stats, s));
@@ -767,6 +768,7 @@ int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return MOFEM_E_ARG;
     if (!strcmp(name, "l2_persist")) { ctx->l2_persist = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "cell_kernel")) { ctx->cell_kernel = (int)value; return MOFEM_OK; }   // takes effect at the next mofem_symbolic
     return ctx_fail(ctx, MOFEM_E_ARG, std::string("mofem_set_option: unknown option ") + name);
 }
 

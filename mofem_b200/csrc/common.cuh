@@ -21,6 +21,7 @@ constexpr int N_CLASS = 8 + 32;
 // tasks of one class are further grouped by (diagonal / off-diagonal, triangle count) so that the threads of a warp
 // run the same trip counts; a bucket id is class * N_SUB + sub
 constexpr int N_SUB = 16;
+constexpr int FAST_CLASS = 5;   // quad4 overlay cells on the warp-cooperative cell kernel (sub-bucket 0 = first task of a cell)
 constexpr int N_BUCKET = N_CLASS * N_SUB;
 __host__ __device__ inline int type_index(int nn) { return nn == 3 ? 0 : nn == 4 ? 1 : nn == 6 ? 2 : 3; }
 
@@ -65,7 +66,7 @@ cudaError_t exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n
 cudaError_t launch_cell_counts(const DevProblem &p, int32_t *ntask, int32_t *npair, int32_t *ncoo, int *err_flag,
                                cudaStream_t s);
 cudaError_t launch_fill_tasks(const DevProblem &p, const int64_t *task_off, const int64_t *pair_off,
-                              const DevTasks &t, cudaStream_t s);
+                              const DevTasks &t, int use_fast, cudaStream_t s);
 cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS] dev, zeroed*/,
                                 const int64_t *cls_start /*[N_CLASS] dev or null*/, int32_t *cls_tasks,
                                 int phase, cudaStream_t s);

@@ -164,8 +164,24 @@ __device__ __forceinline__ int task_class(const DevProblem &p, int64_t c, int n1
     return 8 + 2 * (4 * type_index(n1) + type_index(n2)) + curved;
 }
 
-__device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n1, int n2, bool regular, bool diag)
+// Cells whose incident elements are one or two 4-node quads, integrated over straight triangles, take the warp-cooperative
+// cell kernel (k_cell_q4): all their tasks go to class FAST_CLASS, sub-bucket 0 = the first task of the cell.
+__device__ __forceinline__ bool cell_is_fast(const DevProblem &p, int64_t c)
 {
+    if (p.cell_kind[c] != CELL_OVERLAY) return false;
+    const int32_t *ce = p.cell_elem + c * p.n_mesh;
+    int ne = 0;
+    for (int j = 0; j < p.n_mesh; j++)
+        if (ce[j] >= 0) { if (p.elem_nn[ce[j]] != 4) return false; ne++; }
+    if (ne < 1 || ne > 2) return false;
+    if (p.tri_curved)
+        for (int64_t t = p.cell_tri_ptr[c]; t < p.cell_tri_ptr[c + 1]; t++) if (p.tri_curved[t]) return false;
+    return p.cell_tri_ptr[c + 1] > p.cell_tri_ptr[c];
+}
+
+__device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n1, int n2, bool regular, bool diag, int fast = 0)
+{
+    if (fast) return FAST_CLASS * N_SUB + (fast == 1 ? 0 : 1);
     const int cls = task_class(p, c, n1, n2, regular);
     int sub = 0;
     if (!regular) {
@@ -176,7 +192,7 @@ __device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n
 }
 
 __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off, const int64_t *__restrict__ pair_off,
-                             DevTasks t)
+                             DevTasks t, int use_fast)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n_cell) return;
@@ -193,17 +209,19 @@ __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off,
             }
         return;
     }
+    const bool fast = use_fast && cell_is_fast(p, c);
+    const int64_t k0 = k;
     for (int j = 0; j < M; j++) {
         if (ce[j] < 0) continue;
         int n1 = p.elem_nn[ce[j]];
         t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[j]; t.slots[k] = j | (j << 8);
-        t.cls[k] = task_bucket(p, c, n1, n1, false, true); t.pair_off[k] = po;
+        t.cls[k] = task_bucket(p, c, n1, n1, false, true, fast ? (k == k0 ? 1 : 2) : 0); t.pair_off[k] = po;
         k++; po += n1 * n1;
         for (int l = j + 1; l < M; l++) {
             if (ce[l] < 0) continue;
             int n2 = p.elem_nn[ce[l]];
             t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[l]; t.slots[k] = j | (l << 8);
-            t.cls[k] = task_bucket(p, c, n1, n2, false, false); t.pair_off[k] = po;
+            t.cls[k] = task_bucket(p, c, n1, n2, false, false, fast ? 2 : 0); t.pair_off[k] = po;
             k++; po += n1 * n2;
         }
     }
@@ -236,10 +254,10 @@ cudaError_t launch_cell_counts(const DevProblem &p, int32_t *ntask, int32_t *npa
 }
 
 cudaError_t launch_fill_tasks(const DevProblem &p, const int64_t *task_off, const int64_t *pair_off,
-                              const DevTasks &t, cudaStream_t s)
+                              const DevTasks &t, int use_fast, cudaStream_t s)
 {
     if (p.n_cell == 0) return cudaSuccess;
-    k_fill_tasks<<<(unsigned)((p.n_cell + 255) / 256), 256, 0, s>>>(p, task_off, pair_off, t);
+    k_fill_tasks<<<(unsigned)((p.n_cell + 255) / 256), 256, 0, s>>>(p, task_off, pair_off, t, use_fast);
     return cudaGetLastError();
 }
 
@@ -386,6 +404,140 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
         for (int ab = 0; ab < N1 * N2; ab++) store_pair(out + 4 * ab, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
     }
     // statistics: warp-reduce then one atomic per warp (integers: order-independent)
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        newton += __shfl_xor_sync(0xffffffffu, newton, d);
+        evals += __shfl_xor_sync(0xffffffffu, evals, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (newton) atomicAdd(&stats[0], newton);
+        if (evals) atomicAdd(&stats[1], evals);
+    }
+    if (fail) stats[2] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative cell kernel for the dominant case: overlay cells whose incident elements are one or two 4-node quads,
+// straight integration triangles (stiffnessMatrix.lowerOrderAMORE:99 / quadraticAMORE:131 with n1 + n2 = 8 -> 6 points).
+//
+// Half a warp (16 lanes) owns one cell.
+//   phase 1  lane q < 16 takes integration point q of the round (points are numbered triangle-major, 6 per triangle):
+//            position, weights rho, ONE evaluation per incident element (Newton inverse map + shape gradients) -- the
+//            reference evaluates element j for its diagonal block and again for the off-diagonal block; the values are
+//            identical, so each (point, element) pair is evaluated once here -- and writes w*g and g of both elements
+//            to shared memory (32 doubles per point).
+//   phase 2  lane t < 4 * (blocks of the cell) owns row-node a of one block (diag j | off (j,l) | diag l) and accumulates
+//            its 4 x 4 sums over the points of the round IN POINT ORDER with the same fma sequence as k_amore, so the
+//            results are bit-identical to the thread-per-block kernel.
+// Geometry is staged through shared memory, the per-cell reduction is a shared-memory transpose (no atomics).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CELLQ_THREADS = 128;            // 8 cells per block
+constexpr int CELLQ_PT_DOUBLES = 32;          // per point: wg1x[4] wg1y[4] g1x[4] g1y[4] wg2x[4] wg2y[4] g2x[4] g2y[4]
+
+__global__ void __launch_bounds__(CELLQ_THREADS)
+k_cell_q4(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n_cells, double *__restrict__ blk_val,
+          unsigned long long *__restrict__ stats)
+{
+    __shared__ double pts[CELLQ_THREADS / 16][16][CELLQ_PT_DOUBLES];
+    const int lane = threadIdx.x & 15, slot = threadIdx.x >> 4;
+    const int64_t ci = (int64_t)blockIdx.x * (CELLQ_THREADS / 16) + slot;
+    const bool live = ci < n_cells;
+    unsigned long long newton = 0, evals = 0;
+    bool fail = false;
+    int64_t k0 = 0, c = 0;
+    int e1 = 0, e2 = 0, sj = 0, sl = 0, ne = 1;
+    if (live) {
+        k0 = first_task[ci];
+        c = t.cell[k0];
+        e1 = t.e1[k0]; sj = t.slots[k0] & 0xff;
+        // a second incident element shows up as the off-diagonal task right after the diagonal one
+        if (k0 + 1 < t.n_task && t.cell[k0 + 1] == c) { ne = 2; e2 = t.e2[k0 + 1]; sl = t.slots[k0 + 1] >> 8; }
+        else { e2 = e1; sl = sj; }
+    }
+    double X1[4], Y1[4], X2[4], Y2[4];
+    if (live) { load_elem<4>(p, e1, X1, Y1); load_elem<4>(p, e2, X2, Y2); }
+    const int64_t tr0 = live ? p.cell_tri_ptr[c] : 0;
+    const int npts = live ? (int)(p.cell_tri_ptr[c + 1] - tr0) * 6 : 0;
+    const int M = p.n_mesh;
+    const int qoff = tri_rule_offset(6);
+    // phase-2 role of this lane
+    const int n_out = ne == 2 ? 12 : 4;
+    const int blk = lane >> 2, a = lane & 3;          // blk 0: diag j, 1: off (j,l), 2: diag l
+    const int wsrc = (blk == 2) ? 16 : 0;             // w*g of element l for the last block, of element j otherwise
+    const int gsrc = (blk == 0) ? 8 : 24;             // g of element j for the first block, of element l otherwise
+    double S[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) S[i] = 0.0;
+    // all 32 lanes of the warp run the same number of rounds (the two cells of a warp may differ)
+    const int npts_other = __shfl_xor_sync(0xffffffffu, npts, 16);
+    const int rounds = ((npts > npts_other ? npts : npts_other) + 15) >> 4;
+    for (int r = 0; r < rounds; r++) {
+        const int q = r * 16 + lane;
+        if (q < npts) {
+            const int64_t tr = tr0 + q / 6;
+            const int kq = q % 6;
+            double tx[3], ty[3], rho1[3], rho2[3];
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                tx[v] = p.tri_xy[6 * tr + 2 * v]; ty[v] = p.tri_xy[6 * tr + 2 * v + 1];
+                rho1[v] = p.tri_rho[(3 * tr + v) * M + sj];
+                rho2[v] = p.tri_rho[(3 * tr + v) * M + sl];
+            }
+            TriPoint tp;
+            tri_straight(tx, ty, tp);
+            double dr1x, dr1y, dr2x = 0.0, dr2y = 0.0;
+            tri_grad_rho(tp, rho1, dr1x, dr1y);
+            if (ne == 2) tri_grad_rho(tp, rho2, dr2x, dr2y);
+            const double L1 = c_tp[3 * (qoff + kq)], L2 = c_tp[3 * (qoff + kq) + 1];
+            const double wq = c_tw[qoff + kq];
+            double Nt[3] = {L1, L2, 1.0 - L1 - L2};
+            const double x = dot_vecmat<3>(Nt, tx), y = dot_vecmat<3>(Nt, ty);
+            const double r1v = dot_gemm<3>(Nt, rho1);
+            const double w = 0.5 * tp.detJ * wq;
+            double gx[4], gy[4];
+            int it = strain_pair<4>(X1, Y1, x, y, r1v, dr1x, dr1y, gx, gy);
+            if (it < 0) fail = true; else newton += (unsigned long long)it * (ne == 2 ? 2 : 1);   // the reference evaluates twice
+            evals += (ne == 2 ? 2 : 1);
+            double *row = pts[slot][lane];
+#pragma unroll
+            for (int b = 0; b < 4; b++) { row[b] = w * gx[b]; row[4 + b] = w * gy[b]; row[8 + b] = gx[b]; row[12 + b] = gy[b]; }
+            if (ne == 2) {
+                const double r2v = dot_gemm<3>(Nt, rho2);
+                it = strain_pair<4>(X2, Y2, x, y, r2v, dr2x, dr2y, gx, gy);
+                if (it < 0) fail = true; else newton += 2ull * it;
+                evals += 2;
+#pragma unroll
+                for (int b = 0; b < 4; b++) { row[16 + b] = w * gx[b]; row[20 + b] = w * gy[b]; row[24 + b] = gx[b]; row[28 + b] = gy[b]; }
+            }
+        }
+        __syncwarp();
+        if (live && lane < n_out) {
+            const int nq = npts - r * 16 < 16 ? npts - r * 16 : 16;
+            for (int qq = 0; qq < nq; qq++) {
+                const double *row = pts[slot][qq];
+                const double wx = row[wsrc + a], wy = row[wsrc + 4 + a];
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const double g2x = row[gsrc + b], g2y = row[gsrc + 4 + b];
+                    S[4 * b + 0] = fma(wx, g2x, S[4 * b + 0]);
+                    S[4 * b + 1] = fma(wx, g2y, S[4 * b + 1]);
+                    S[4 * b + 2] = fma(wy, g2x, S[4 * b + 2]);
+                    S[4 * b + 3] = fma(wy, g2y, S[4 * b + 3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (live && lane < n_out) {
+        // diag j and off (j,l) use element j's material (AMORE.py:113), diag l its own
+        const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[blk == 2 ? e2 : e1];
+        double D[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) D[i] = Dp[i];
+        double *out = blk_val + 4 * (t.pair_off[k0 + blk] + 4 * a);
+#pragma unroll
+        for (int b = 0; b < 4; b++) store_pair(out + 4 * b, D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3]);
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         newton += __shfl_xor_sync(0xffffffffu, newton, d);
@@ -562,6 +714,10 @@ cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks 
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
+    if (cls == FAST_CLASS) {
+        k_cell_q4<<<(unsigned)((n + CELLQ_THREADS / 16 - 1) / (CELLQ_THREADS / 16)), CELLQ_THREADS, 0, s>>>(p, t, list, n, blk_val, stats);
+        return cudaGetLastError();
+    }
     if (cls < 8) {
         switch (cls) {
         case 0: k_regular<3><<<grid, 128, 0, s>>>(p, t, list, n, blk_val); break;
