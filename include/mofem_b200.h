@@ -165,8 +165,9 @@ int mofem_p2p_close(mofem_ctx *ctx);
  * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */
 int mofem_set_profile(mofem_ctx *ctx, int on);
-/* Tuning switches: "l2_persist" (default 1) pins the PCG vectors in L2 during mofem_solve; "cell_kernel" (default 1)
- * sends quad4 overlay cells to the warp-cooperative cell kernel (bit-identical results; set before mofem_symbolic). */
+/* Tuning switches: "l2_persist" (default 1) pins the PCG vectors in L2 during mofem_solve; "cell_kernel" (default 0)
+ * sends quad4 overlay cells to the warp-cooperative cell kernel instead of the thread-per-block kernels (bit-identical
+ * results, measured slower on B200 -- see DESIGN.md; set before mofem_symbolic). */
 int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value);
 int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations);
 

@@ -434,7 +434,7 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
 constexpr int CELLQ_THREADS = 128;            // 8 cells per block
 constexpr int CELLQ_PT_DOUBLES = 32;          // per point: wg1x[4] wg1y[4] g1x[4] g1y[4] wg2x[4] wg2y[4] g2x[4] g2y[4]
 
-__global__ void __launch_bounds__(CELLQ_THREADS)
+__global__ void __launch_bounds__(CELLQ_THREADS, 4)
 k_cell_q4(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n_cells, double *__restrict__ blk_val,
           unsigned long long *__restrict__ stats)
 {

@@ -109,3 +109,20 @@ def test_spmv_matches_scipy(gpu_ctx):
     y = gpu_ctx.spmv(x)
     yr = K @ x
     assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+
+
+@pytest.mark.parametrize("name", ["patch16", "patch16_m3", "simpleOFE3", "zoo_s1"])
+def test_cell_kernel_is_bit_identical_to_the_block_kernels(gpu_ctx, name):
+    """The warp-cooperative quad4 cell kernel (one evaluation per point and element, shared-memory transpose) keeps the
+    per-block kernels' fma order: identical bits, identical Newton counts."""
+    fp, d = load_golden(name)
+    gpu_ctx.set_option("cell_kernel", 0)
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    a, na = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"]
+    gpu_ctx.set_option("cell_kernel", 1)
+    try:
+        gpu_ctx.set_problem(fp).symbolic().assemble()
+        b, nb = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"]
+    finally:
+        gpu_ctx.set_option("cell_kernel", 0)
+    assert np.array_equal(a, b) and na == nb
