@@ -224,14 +224,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (mofem_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
 
     # ---- untimed preprocessing: the flattened overlay (what the plane sweep + flatten() hand to the solver) ------
     # N > 1 (weak scaling): the domain is a stack of N blocks of n0 x n0 mesh-0 elements; rank r owns block r (its
     # mesh-0 node rows and the patches inside) and generates only the cells that touch its nodes.
+    # (Generation forks worker processes, so it runs before any CUDA / NCCL initialisation.)
     t0 = time.perf_counter()
     part = None
     n_cells_global = None
@@ -253,15 +250,21 @@ def main():
         for r in range(1, world):
             nd = r * args.n0 * (args.n0 + 1) + args.n0
             rhs_g[2 * nd] = 1.0; rhs_g[2 * nd + 1] = -0.5
-        part = exchange_send_lists(partition_problem(strip, owner, rank, world))
+        part = partition_problem(strip, owner, rank, world)
         fp = part.fp
         rhs, fixed, val = part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g)
         # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
         own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)
+        del strip, rhs_g, fixed_g, val_g, owner
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        exchange_send_lists(part)
         t = torch.tensor([own_cells], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         n_cells_global = int(t.item())
-        del strip, rhs_g, fixed_g, val_g, owner
     prep_s = time.perf_counter() - t0
     log(f"[rank {rank}] generated n0={args.n0}: {fp.n_cell} cells, {fp.n_tri} triangles, {fp.n_dof} local DOF in {prep_s:.1f}s")
 

@@ -116,21 +116,28 @@ def _quad_shape(r, s):
     return N, dr, ds
 
 
-def _inv_quad_N(coord, xy, iters=8):
-    """Shape-function values N_a(xi(xy)) of quad4 elements (Newton inverse map, invShapeFunction.py:41-73)."""
-    c0 = coord[..., :1, :]
-    cn = coord - c0
-    x = xy - c0[..., 0, :]
-    r = np.zeros(xy.shape[:-1]); s = np.zeros(xy.shape[:-1])
+def _inv_quad_N(coord, xy, iters=6):
+    """Shape-function values N_a(xi(xy)) of quad4 elements (Newton inverse map, invShapeFunction.py:41-73), vectorised
+    over the leading axis with explicit bilinear formulas (6 updates from (0,0): the jittered quads converge in 3-5)."""
+    X = coord[..., 0] - coord[..., :1, 0]
+    Y = coord[..., 1] - coord[..., :1, 1]
+    x = xy[..., 0] - coord[..., 0, 0]
+    y = xy[..., 1] - coord[..., 0, 1]
+    X0, X1, X2, X3 = (X[..., k] for k in range(4))
+    Y0, Y1, Y2, Y3 = (Y[..., k] for k in range(4))
+    r = np.zeros_like(x); s = np.zeros_like(x)
     for _ in range(iters):
-        N, dr, ds = _quad_shape(r, s)
-        res = x - np.einsum("...a,...ad->...d", N, cn)
-        j00 = np.einsum("...a,...a->...", dr, cn[..., 0]); j01 = np.einsum("...a,...a->...", ds, cn[..., 0])
-        j10 = np.einsum("...a,...a->...", dr, cn[..., 1]); j11 = np.einsum("...a,...a->...", ds, cn[..., 1])
-        det = j00 * j11 - j01 * j10
-        r = r + (res[..., 0] * j11 - res[..., 1] * j01) / det
-        s = s + (-res[..., 0] * j10 + res[..., 1] * j00) / det
-    return _quad_shape(r, s)[0]
+        rm, rp, sm, sp = 1.0 - r, 1.0 + r, 1.0 - s, 1.0 + s
+        N0, N1, N2, N3 = 0.25 * rm * sm, 0.25 * rp * sm, 0.25 * rp * sp, 0.25 * rm * sp
+        fx = x - (N0 * X0 + N1 * X1 + N2 * X2 + N3 * X3)
+        fy = y - (N0 * Y0 + N1 * Y1 + N2 * Y2 + N3 * Y3)
+        xr = 0.25 * (sm * (X1 - X0) + sp * (X2 - X3)); xs = 0.25 * (rm * (X3 - X0) + rp * (X2 - X1))
+        yr = 0.25 * (sm * (Y1 - Y0) + sp * (Y2 - Y3)); ys = 0.25 * (rm * (Y3 - Y0) + rp * (Y2 - Y1))
+        det = xr * ys - xs * yr
+        r = r + (fx * ys - fy * xs) / det
+        s = s + (fy * xr - fx * yr) / det
+    rm, rp, sm, sp = 1.0 - r, 1.0 + r, 1.0 - s, 1.0 + s
+    return np.stack([0.25 * rm * sm, 0.25 * rp * sm, 0.25 * rp * sp, 0.25 * rm * sp], -1)
 
 
 def _point_gt(a, b):
@@ -215,6 +222,68 @@ def _quad_triangles(poly):
     return idx
 
 
+_RING_CTX = None
+
+
+def _gen_workers(n_patches):
+    import os
+    w = os.environ.get("MOFEM_GEN_WORKERS")
+    if w is not None:
+        return max(1, int(w))
+    if n_patches < 4000:
+        return 1
+    return max(1, min(8, (os.cpu_count() or 1) // 2))
+
+
+def _ring_row(c, bb):
+    """Ring cells of patch row ``bb``: (bb, element ids, triangle coordinates [T,3,2], triangles per cell)."""
+    IW, IE, IS, IN, X0, X1 = c["IW"], c["IE"], c["IS"], c["IN"], c["X0"], c["X1"]
+    b_lo, Px, nx = c["b_lo"], c["Px"], c["nx"]
+    j1 = PERIOD * bb + 1
+    X0l = X0[j1:j1 + 7].tolist()                      # the 7 mesh-0 node rows this patch row touches
+    elems, tris_out, cnt = [], [], []
+    for aa in range(Px):
+        iw = IW[bb - b_lo, aa, :, 0].tolist(); ie = IE[bb - b_lo, aa, :, 4].tolist()
+        is_ = IS[bb - b_lo, aa, 0, :].tolist(); in_ = IN[bb - b_lo, aa, 4, :].tolist()
+        m = X1[bb, aa].tolist()
+        i1 = PERIOD * aa + 1
+        polys = []
+
+        def corners(u, v):
+            i = i1 + u
+            return X0l[v][i], X0l[v][i + 1], X0l[v + 1][i + 1], X0l[v + 1][i]
+        for v in range(1, 5):      # left and right sides
+            n00, n10, n11, n01 = corners(0, v)
+            polys.append((0, v, [n00, iw[v - 1], m[v][0], iw[v], n01]))
+            n00, n10, n11, n01 = corners(5, v)
+            polys.append((5, v, [ie[v - 1], n10, n11, ie[v], m[v][5]]))
+        for u in range(1, 5):      # bottom and top sides
+            n00, n10, n11, n01 = corners(u, 0)
+            polys.append((u, 0, [n00, n10, is_[u], m[0][u], is_[u - 1]]))
+            n00, n10, n11, n01 = corners(u, 5)
+            polys.append((u, 5, [in_[u - 1], m[5][u], in_[u], n11, n01]))
+        n00, n10, n11, n01 = corners(0, 0)
+        polys.append((0, 0, [n00, n10, is_[0], m[0][0], iw[0], n01]))
+        n00, n10, n11, n01 = corners(5, 0)
+        polys.append((5, 0, [n00, n10, n11, ie[0], m[0][5], is_[4]]))
+        n00, n10, n11, n01 = corners(5, 5)
+        polys.append((5, 5, [ie[4], n10, n11, n01, in_[4], m[5][5]]))
+        n00, n10, n11, n01 = corners(0, 5)
+        polys.append((0, 5, [n00, iw[4], m[5][0], in_[0], n11, n01]))
+        for u, v, poly in polys:
+            tris = ear_triangulate(poly)
+            elems.append((j1 + v) * nx + i1 + u)
+            for t in tris:
+                tris_out.append([poly[t[0]], poly[t[1]], poly[t[2]]])
+            cnt.append(len(tris))
+    return (bb, np.array(elems, dtype=np.int64), np.array(tris_out, dtype=np.float64).reshape(-1, 3, 2),
+            np.array(cnt, dtype=np.int64))
+
+
+def _ring_rows_worker(rows):
+    return [_ring_row(_RING_CTX, bb) for bb in rows]
+
+
 def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
                  solver: int = SOLVER_LOWER, return_meshes: bool = False, ny: int = None, patch_rows=None,
                  n_mesh: int = 2):
@@ -279,16 +348,14 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     w1 = np.zeros((6, 6)); w1[1:5, 1:5] = 1.0
     node_w = np.concatenate([np.ones(pm.n_node0), np.tile(w1.reshape(-1), Px * Py)])
 
-    c0 = node_xy[en0[e0_piece]]                                   # [n_piece,4,2]
-    c1 = node_xy[en1[e1_piece - n_elem0]]
+    c1 = node_xy[en1[e1_piece - n_elem0]]                         # [n_piece,4,2]
     wgt1 = node_w[en1[e1_piece - n_elem0]]                        # [n_piece,4]
     patch_mesh = (1 + ((b + a) % 2 if n_mesh == 3 else 0 * b))            # [Py',Px,5,5] mesh of the patch
     mesh_piece = np.broadcast_to(patch_mesh[..., None], (b_hi - b_lo, Px, 5, 5, 4)).reshape(-1)
     rho_piece = np.zeros((n_piece, 4, n_mesh))
     for v in range(4):
-        N0 = _inv_quad_N(c0, pieces[:, v])
         N1 = _inv_quad_N(c1, pieces[:, v])
-        r0 = N0.sum(-1)                                           # weights of mesh 0 are all 1
+        r0 = 1.0          # mesh 0: every node weight is 1 and the shape functions sum to 1 (the reference gets 1 +- 1 ulp)
         r1 = 9.0 * (N1 * wgt1).sum(-1)
         rho_piece[:, v, 0] = r0 / (r0 + r1)
         rho_piece[np.arange(n_piece), v, mesh_piece] = r1 / (r0 + r1)
@@ -298,45 +365,32 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     piece_tri_rho = rho_piece[ar, tri_idx]                        # [n_piece,2,3,n_mesh]
 
     # ---- ring cells (one element, triangulated) -----------------------------------------------
-    ring_elem, ring_tri_xy, ring_ptr = [], [], [0]
-    X0l = X0.tolist()
-    for bb in range(b_lo, b_hi):
-        for aa in range(Px):
-            iw = IW[bb - b_lo, aa, :, 0].tolist(); ie = IE[bb - b_lo, aa, :, 4].tolist()
-            is_ = IS[bb - b_lo, aa, 0, :].tolist(); in_ = IN[bb - b_lo, aa, 4, :].tolist()
-            m = X1[bb, aa].tolist()
-            i1, j1 = PERIOD * aa + 1, PERIOD * bb + 1
-            polys = []
-
-            def corners(u, v):
-                i, j = i1 + u, j1 + v
-                return X0l[j][i], X0l[j][i + 1], X0l[j + 1][i + 1], X0l[j + 1][i]
-            for v in range(1, 5):      # left and right sides
-                n00, n10, n11, n01 = corners(0, v)
-                polys.append((0, v, [n00, iw[v - 1], m[v][0], iw[v], n01]))
-                n00, n10, n11, n01 = corners(5, v)
-                polys.append((5, v, [ie[v - 1], n10, n11, ie[v], m[v][5]]))
-            for u in range(1, 5):      # bottom and top sides
-                n00, n10, n11, n01 = corners(u, 0)
-                polys.append((u, 0, [n00, n10, is_[u], m[0][u], is_[u - 1]]))
-                n00, n10, n11, n01 = corners(u, 5)
-                polys.append((u, 5, [in_[u - 1], m[5][u], in_[u], n11, n01]))
-            n00, n10, n11, n01 = corners(0, 0)
-            polys.append((0, 0, [n00, n10, is_[0], m[0][0], iw[0], n01]))
-            n00, n10, n11, n01 = corners(5, 0)
-            polys.append((5, 0, [n00, n10, n11, ie[0], m[0][5], is_[4]]))
-            n00, n10, n11, n01 = corners(5, 5)
-            polys.append((5, 5, [ie[4], n10, n11, n01, in_[4], m[5][5]]))
-            n00, n10, n11, n01 = corners(0, 5)
-            polys.append((0, 5, [n00, iw[4], m[5][0], in_[0], n11, n01]))
-            for u, v, poly in polys:
-                tris = ear_triangulate(poly)
-                ring_elem.append(elem0(j1 + v, i1 + u))
-                for t in tris:
-                    ring_tri_xy.append([poly[t[0]], poly[t[1]], poly[t[2]]])
-                ring_ptr.append(len(ring_tri_xy))
-    ring_elem = np.array(ring_elem, dtype=np.int64)
-    ring_tri_xy = np.array(ring_tri_xy, dtype=np.float64).reshape(-1, 3, 2)
+    # scalar work (the reference's recursive ear rule per polygon): spread over forked worker processes when large
+    ctx_ring = dict(IW=IW, IE=IE, IS=IS, IN=IN, X0=X0, X1=X1, b_lo=b_lo, Px=Px, nx=nx)
+    rows = list(range(b_lo, b_hi))
+    n_workers = _gen_workers(len(rows) * Px)
+    if n_workers > 1:
+        import multiprocessing as mp
+        global _RING_CTX
+        _RING_CTX = ctx_ring
+        chunks = [rows[k::n_workers * 4] for k in range(n_workers * 4)]
+        order = np.argsort(np.concatenate([c for c in chunks if c]), kind="stable")
+        with mp.get_context("fork").Pool(n_workers) as pool:
+            parts = pool.map(_ring_rows_worker, [c for c in chunks if c])
+        _RING_CTX = None
+        # back to ascending patch-row order (each part holds whole rows)
+        by_row = {}
+        for part in parts:
+            for bb, elems, tris, cnt in part:
+                by_row[bb] = (elems, tris, cnt)
+        del order
+        parts_sorted = [by_row[bb] for bb in rows]
+    else:
+        parts_sorted = [_ring_row(ctx_ring, bb)[1:] for bb in rows]
+    ring_elem = np.concatenate([p[0] for p in parts_sorted]) if parts_sorted else np.zeros(0, np.int64)
+    ring_tri_xy = np.concatenate([p[1] for p in parts_sorted]).reshape(-1, 3, 2) if parts_sorted else np.zeros((0, 3, 2))
+    ring_cnt = np.concatenate([p[2] for p in parts_sorted]) if parts_sorted else np.zeros(0, np.int64)
+    ring_ptr = np.concatenate([[0], np.cumsum(ring_cnt)])
     n_ring = len(ring_elem)
 
     # ---- untouched mesh-0 elements -> regular quadFE cells ------------------------------------------
@@ -359,7 +413,7 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     cell_elem[n_reg + n_ring:, 0] = e0_piece
     cell_elem[n_reg + n_ring + np.arange(n_piece), mesh_piece] = e1_piece
     ntri = np.zeros(C, dtype=np.int64)
-    ntri[n_reg:n_reg + n_ring] = np.diff(np.array(ring_ptr))
+    ntri[n_reg:n_reg + n_ring] = ring_cnt
     ntri[n_reg + n_ring:] = 2
     tri_ptr = np.concatenate([[0], np.cumsum(ntri)])
     ring_rho = np.zeros((len(ring_tri_xy), 3, n_mesh)); ring_rho[:, :, 0] = 1.0
