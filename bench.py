@@ -383,11 +383,16 @@ def main():
     iters = max(prof["iterations"], 1)
     spmv_ms = prof["spmv_ms"] / iters if prof["iterations"] else None
     roofline = None
+    traffic = None    # dram__bytes_read + dram__bytes_write per SpMV launch, from the committed ncu capture of this workload
+    tpath = os.path.join(REPO, "profiles", "r1_spmv_traffic.json")
+    if world == 1 and args.n0 == 664 and args.meshes == 2 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
     if spmv_ms:
         ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
         roofline = {"kernel": "k_spmv (block-CSR SpMV inside Jacobi-PCG)", "bound": "hbm", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": ab["spmv"], "avg_launch_ms": spmv_ms,
                     "scalar_csr_equivalent_gbs": ab["spmv_scalar_csr"] / (spmv_ms * 1e-3) / 1e9,
                     "share_of_step": prof["spmv_ms"] / args.steps / step_ms}
