@@ -64,6 +64,58 @@ k_rows(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
     }
 }
 
+// ---- variant: as k_rows, node_ptr of the NEXT row prefetched while the current row is processed (software pipelining) --
+template <int LANES, int BLOCK, int MINB, int UNROLL, bool IDXPF>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_rows_pipe(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
+            const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int sub = threadIdx.x % LANES;
+    const int64_t rows_per_block = BLOCK / LANES;
+    const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+    int64_t a = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES;
+    int64_t r0 = 0, r1 = 0;
+    if (a < n_node) { r0 = node_ptr[a]; r1 = node_ptr[a + 1]; }
+    int cpf = 0;
+    if (IDXPF && a < n_node && sub < r1 - r0) cpf = __ldg(node_idx + r0 + sub);
+    for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += stride) {
+        const int64_t an = a + stride;
+        int64_t r0n = 0, r1n = 0;
+        if (an < n_node) { r0n = node_ptr[an]; r1n = node_ptr[an + 1]; }
+        double y0 = 0.0, y1 = 0.0;
+        if (a < n_node) {
+            const int deg = (int)(r1 - r0);
+            const double2 *d0 = reinterpret_cast<const double2 *>(data + 4 * r0);
+            const double2 *d1 = reinterpret_cast<const double2 *>(data + 4 * r0 + 2 * deg);
+            for (int kb = sub; kb < deg; kb += LANES * UNROLL) {
+                double2 v0[UNROLL], v1[UNROLL], xv[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int kk = kb + u * LANES;
+                    if (kk < deg) {
+                        const int c = (IDXPF && u == 0 && kb == sub) ? cpf : __ldg(node_idx + r0 + kk);
+                        v0[u] = __ldcs(d0 + kk); v1[u] = __ldcs(d1 + kk);
+                        xv[u] = __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
+                    } else { v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0); }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    y0 = fma(v0[u].x, xv[u].x, y0); y0 = fma(v0[u].y, xv[u].y, y0);
+                    y1 = fma(v1[u].x, xv[u].x, y1); y1 = fma(v1[u].y, xv[u].y, y1);
+                }
+            }
+        }
+        if (IDXPF && an < n_node && sub < r1n - r0n) cpf = __ldg(node_idx + r0n + sub);
+#pragma unroll
+        for (int d = LANES / 2; d; d >>= 1) {
+            y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+            y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+        }
+        if (a < n_node && sub == 0) *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+        a = an; r0 = r0n; r1 = r1n;
+    }
+}
+
 // ---- variant: values staged through shared memory with 1-D bulk async copies (TMA), thread per block multiply,
 //      thread per row fixed-order sum ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,6 +222,23 @@ int main(int argc, char **argv)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     std::vector<double> yref(2 * n_node), yv(2 * n_node);
     bool have_ref = false;
+    // cold-L2 timing: a 512 MB memset between launches evicts the index / pointer arrays, as the vector kernels of the PCG
+    // loop do between two SpMVs
+    char *flush; CK(cudaMalloc(&flush, 512u << 20));
+    auto run_cold = [&](const char *name, auto launch) {
+        float tot = 0;
+        const int reps = 20;
+        for (int i = 0; i < reps + 2; i++) {
+            CK(cudaMemsetAsync(flush, i, 512u << 20));
+            cudaEventRecord(e0);
+            launch();
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (i >= 2) tot += ms;
+        }
+        printf("COLD %-40s %8.2f us  %7.1f GB/s\n", name, tot / reps * 1e3, bytes / (tot / reps * 1e-3) / 1e9);
+    };
     auto run = [&](const char *name, auto launch) {
         CK(cudaMemset(d_y, 0, n_node * 16));
         for (int i = 0; i < 5; i++) launch();
@@ -190,21 +259,40 @@ int main(int argc, char **argv)
     run("rows lanes=" #L " block=" #B " minb=" #M " stream=" #S " unroll=" #UN " grid=" #G, [&]() {              \
         int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
         k_rows<L, B, M, S, UN><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
-    ROWS(8, 256, 8, false, 1, 8);
-    ROWS(8, 128, 16, true, 2, 0);
-    ROWS(8, 128, 16, false, 2, 0);
-    ROWS(8, 128, 16, true, 3, 0);
-    ROWS(8, 128, 16, true, 4, 0);
+#define ROWS(L, B, M, S, UN, G)                                                                                  \
+    run("rows lanes=" #L " block=" #B " minb=" #M " stream=" #S " unroll=" #UN " grid=" #G, [&]() {              \
+        int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
+        k_rows<L, B, M, S, UN><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
+#define PIPE(L, B, M, UN, PF, G)                                                                                   \
+    run("pipe lanes=" #L " block=" #B " minb=" #M " unroll=" #UN " idxpf=" #PF " grid=" #G, [&]() {               \
+        int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
+        k_rows_pipe<L, B, M, UN, PF><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
+#define COLD_ROWS(L, B, M, S, UN, G)                                                                              \
+    run_cold("rows lanes=" #L " block=" #B " minb=" #M " unroll=" #UN " grid=" #G, [&]() {                          \
+        int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
+        k_rows<L, B, M, S, UN><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
+#define COLD_PIPE(L, B, M, UN, PF, G)                                                                             \
+    run_cold("pipe lanes=" #L " block=" #B " minb=" #M " unroll=" #UN " idxpf=" #PF " grid=" #G, [&]() {           \
+        int64_t g = (n_node + (B / L) - 1) / (B / L); if (G > 0 && g > 148 * G) g = 148 * G;                       \
+        k_rows_pipe<L, B, M, UN, PF><<<(unsigned)g, B>>>(n_node, d_ptr, d_idx, d_data, d_x, d_y); })
+    COLD_ROWS(8, 128, 12, true, 4, 24);
+    COLD_PIPE(8, 128, 12, 4, false, 24);
+    COLD_PIPE(8, 128, 12, 4, true, 24);
+    COLD_PIPE(8, 128, 10, 4, false, 24);
+    COLD_PIPE(8, 128, 10, 4, true, 24);
+    COLD_PIPE(8, 256, 6, 4, false, 12);
+    COLD_ROWS(8, 128, 12, true, 4, 0);
+    COLD_ROWS(16, 128, 12, true, 2, 0);
+    COLD_ROWS(8, 128, 12, true, 4, 24);
+    PIPE(8, 128, 12, 4, false, 24);
+    PIPE(8, 128, 12, 4, true, 24);
+    PIPE(8, 128, 10, 4, false, 24);
+    PIPE(8, 128, 10, 4, true, 24);
+    PIPE(8, 128, 12, 4, false, 48);
+    PIPE(8, 128, 12, 3, false, 24);
+    PIPE(8, 256, 6, 4, false, 12);
+    ROWS(8, 128, 12, true, 4, 24);
     ROWS(8, 128, 12, true, 4, 0);
-    ROWS(8, 128, 8, true, 4, 0);
-    ROWS(8, 64, 32, true, 2, 0);
-    ROWS(8, 64, 32, true, 3, 0);
-    ROWS(16, 128, 16, true, 2, 0);
-    ROWS(8, 128, 16, true, 2, 16);
-    ROWS(8, 128, 16, true, 2, 32);
-    ROWS(8, 128, 16, true, 3, 16);
-    ROWS(8, 256, 8, true, 3, 0);
-
     // TMA-staged variant: tiles of <= TB blocks
     auto make_tiles = [&](int TB) {
         std::vector<int32_t> tr; tr.push_back(0);
