@@ -161,6 +161,15 @@ int mofem_p2p_import(mofem_ctx *ctx, const uint8_t *handles /* world x 64 */, co
                      const int64_t *send_remote_off /* n_neighbor */);
 int mofem_p2p_close(mofem_ctx *ctx);
 
+/* Sampler (post-processing of the solution): replaces plotTools/plotResults.py:getGraphDataFE:137 / getGraphDataOFE:15 as
+ * driven by outputFunctions/writeSolution.py:writeSampleData2D:41.  A "unit" is a regular element / untriangulated cell, or
+ * one integration triangle of an overlay cell, in the problem's cell order.  out[unit][7][nS][nS] = X, Y, U, V, Sxx, Syy, Sxy
+ * at the parent-grid points grid[i], grid[j] (np.linspace(-1, 1, nS) in the reference).  u: displacement (host or device,
+ * NULL = the last mofem_solve).  out == NULL only returns *n_unit.  solver: 2 or 3 (stress recovery of regular 4-node
+ * elements: plain D B u or the ICM form). */
+int mofem_sample(mofem_ctx *ctx, const double *u, int32_t n_sampling, int32_t solver, const double *grid, double *out,
+                 int64_t out_capacity_units, int64_t *n_unit);
+
 /* Per-kernel profile of the PCG loop: when on, every iteration of mofem_solve records CUDA events around its three
  * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */

@@ -16,6 +16,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 SOURCES = {
     "integrate.cu": ["-fmad=false"],
+    "sample.cu": ["-fmad=false"],
     "csr.cu": [],
     "scan.cu": [],
     "pcg.cu": [],

@@ -757,6 +757,62 @@ int mofem_clear_halo(mofem_ctx *ctx)
     return MOFEM_OK;
 }
 
+// ---- sampler --------------------------------------------------------------------
+int mofem_sample(mofem_ctx *ctx, const double *u, int32_t n_sampling, int32_t solver, const double *grid, double *out,
+                 int64_t out_capacity_units, int64_t *n_unit)
+{
+    if (!ctx || !ctx->have_problem || !n_unit) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_sample: call mofem_set_problem first");
+    if (n_sampling < 1 || n_sampling > 64 || (solver != 2 && solver != 3)) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_sample: bad n_sampling / solver");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevProblem P = ctx->P;
+    P.solver = solver;
+    std::vector<void *> tmp;
+    int rc;
+    int32_t *cnt; int64_t *off;
+    if ((rc = dev_alloc(ctx, &cnt, P.n_cell, tmp)) || (rc = dev_alloc(ctx, &off, P.n_cell + 1, tmp))) { free_pool(ctx, tmp); return rc; }
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CKS(sample_count_units(P, cnt, s));
+    CKS(exclusive_scan_i32_to_i64(cnt, off, P.n_cell, off + P.n_cell, s, nullptr));
+    int64_t nu = 0;
+    CKS(cudaMemcpyAsync(&nu, off + P.n_cell, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CKS(cudaStreamSynchronize(s));
+    *n_unit = nu;
+    if (!out) { free_pool(ctx, tmp); return MOFEM_OK; }          // size query
+    if (!grid) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_sample: null grid"); }
+    if (out_capacity_units < nu) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_sample: output buffer too small"); }
+    const int64_t n_dof = 2 * P.n_node, per = (int64_t)n_sampling * n_sampling;
+    int32_t *unit_cell; int64_t *unit_tri; double *grid_d, *out_d = out, *u_d = nullptr;
+    if ((rc = dev_alloc(ctx, &unit_cell, nu, tmp)) || (rc = dev_alloc(ctx, &unit_tri, nu, tmp)) || (rc = dev_alloc(ctx, &grid_d, n_sampling, tmp))) {
+        free_pool(ctx, tmp); return rc;
+    }
+    const double *uu = u;
+    if (!u) {
+        if (!ctx->have_solution) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_ARG, "mofem_sample: no displacement given and no solve done"); }
+        uu = ctx->u;
+    } else if (!is_device_ptr(u)) {
+        if ((rc = dev_alloc(ctx, &u_d, n_dof, tmp))) { free_pool(ctx, tmp); return rc; }
+        CKS(cudaMemcpyAsync(u_d, u, sizeof(double) * n_dof, cudaMemcpyHostToDevice, s));
+        uu = u_d;
+    }
+    const bool out_host = !is_device_ptr(out);
+    if (out_host && (rc = dev_alloc(ctx, &out_d, nu * 7 * per, tmp))) { free_pool(ctx, tmp); return rc; }
+    CKS(cudaMemcpyAsync(grid_d, grid, sizeof(double) * n_sampling, cudaMemcpyDefault, s));
+    CKS(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
+    CKS(sample_fill_units(P, off, unit_cell, unit_tri, s));
+    CKS(sample_run(P, unit_cell, unit_tri, nu, n_sampling, grid_d, uu, out_d, ctx->err_flag, s));
+    int eflag = 0;
+    CKS(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_host) CKS(cudaMemcpyAsync(out, out_d, sizeof(double) * nu * 7 * per, cudaMemcpyDeviceToHost, s));
+    CKS(cudaStreamSynchronize(s));
+#undef CKS
+    free_pool(ctx, tmp);
+    if (eflag == MOFEM_E_NEWTON) return ctx_fail(ctx, MOFEM_E_NEWTON, "Too many iterations!");
+    if (eflag == MOFEM_E_ELEMENT) return ctx_fail(ctx, MOFEM_E_ELEMENT, "sampler: triangular incident elements are not supported (the reference raises ValueError)");
+    if (eflag) return ctx_fail(ctx, MOFEM_E_ARG, "sampler: unsupported solver for a regular 4-node element");
+    return MOFEM_OK;
+}
+
 int mofem_set_profile(mofem_ctx *ctx, int on)
 {
     if (!ctx) return MOFEM_E_ARG;

@@ -96,6 +96,12 @@ cudaError_t csr_emit(int64_t n_node, const int64_t *row_start, const uint64_t *e
 cudaError_t csr_numeric(const DevCsr &c, const double *blk_val, double *data, cudaStream_t s);
 cudaError_t csr_export_pattern(const DevCsr &c, int32_t *indptr, int32_t *indices, cudaStream_t s);
 
+// sample.cu
+cudaError_t sample_count_units(const DevProblem &p, int32_t *cnt, cudaStream_t s);
+cudaError_t sample_fill_units(const DevProblem &p, const int64_t *unit_off, int32_t *unit_cell, int64_t *unit_tri, cudaStream_t s);
+cudaError_t sample_run(const DevProblem &p, const int32_t *unit_cell, const int64_t *unit_tri, int64_t n_unit, int nS,
+                       const double *grid, const double *u, double *out, int *err, cudaStream_t s);
+
 // pcg.cu
 struct DevSystem {
     int64_t n;            // local scalar unknowns (2 * local nodes, ghosts included)

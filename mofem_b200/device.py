@@ -212,6 +212,18 @@ class Context:
         self._ck(self._L.mofem_clear_halo(self._h))
         return self
 
+    def sample(self, n_sampling: int, solver: int, displacement=None):
+        """Sampler on the current problem: array [n_unit, 7, nS, nS] = X, Y, U, V, Sxx, Syy, Sxy per unit (regular element or
+        integration triangle, in cell order) at the parent-grid points ``np.linspace(-1, 1, nS)``."""
+        grid = np.ascontiguousarray(np.linspace(-1, 1, n_sampling))
+        nu = C.c_int64(0)
+        self._ck(self._L.mofem_sample(self._h, None, int(n_sampling), int(solver), None, None, 0, C.byref(nu)))
+        out = np.empty((nu.value, 7, n_sampling, n_sampling))
+        u = None if displacement is None else _c(np.asarray(displacement).reshape(-1), np.float64)
+        self._ck(self._L.mofem_sample(self._h, _lib.ptr(u), int(n_sampling), int(solver), _lib.ptr(grid), _lib.ptr(out),
+                                      int(nu.value), C.byref(nu)))
+        return out
+
     def set_option(self, name: str, value: int):
         self._ck(self._L.mofem_set_option(self._h, name.encode(), int(value)))
         return self

@@ -223,6 +223,20 @@ def run_amore(stem, input_data=None):
         with Capture() as cap:
             out = fn(input_data, overlapping_mesh, polygons, nep)
     disp, energy = out[0], out[1]
+    sample = None
+    if solver in (2, 3):      # femMain.py:103,112 -- the stress / displacement sampler on the solution
+        import tempfile
+        from outputFunctions import writeSolution
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    writeSolution.writeSampleData2D(input_data[5], input_data[3], polygons, disp, out[2], input_data[4],
+                                                    component='All', nSampling=3, solver=solver)
+                sample = np.loadtxt("SampleData.txt")
+            finally:
+                os.chdir(cwd)
     I, J, V = cap.coo
     # cross-check: array-level path on OUR flattening reproduces the entry-point triplets
     I2, J2, V2 = reference_array_level(fp)
@@ -234,6 +248,8 @@ def run_amore(stem, input_data=None):
                  red_rhs=fr.reshape(-1), red_x=xr.reshape(-1),
                  constraints=np.array(constraints_in, dtype=np.float64),
                  graph=np.frombuffer(pickle.dumps(graph, protocol=4), dtype=np.uint8))
+    if sample is not None:
+        extra["sample_all"] = sample
     print(stem, "cells", fp.n_cell, "tris", fp.n_tri, "coo", len(V), "energy", float(np.array(energy).reshape(-1)[0]))
     return pack(fp, I, J, V, extra), (input_data, overlapping_mesh, polygons, nep)
 
