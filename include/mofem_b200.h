@@ -170,6 +170,17 @@ int mofem_p2p_close(mofem_ctx *ctx);
 int mofem_sample(mofem_ctx *ctx, const double *u, int32_t n_sampling, int32_t solver, const double *grid, double *out,
                  int64_t out_capacity_units, int64_t *n_unit);
 
+/* Weight functions of the overlay vertices: replaces the per-vertex body of
+ * computGeometry/planeSweepMeshes.py:rhoCalculation:991-1030.  vert_xy [n_vert][2]; vert_elem [n_vert][n_mesh] = incident element
+ * (index into the elem_* tables) of mesh slot m of the face that first visits the vertex, -1 = none; elem_nv [n_elem] = 3 or 4
+ * corner vertices (element.vertex), elem_xy [n_elem][4][2] their coordinates, elem_w [n_elem][4] their weights (1, or 0 on a
+ * mesh boundary inside the domain, planeSweepMeshes.py:434-446).  rho [n_vert][n_mesh] (host or device, like every input):
+ * interpolated weight per slot, slots >= 1 times 9, row normalised by its sum.  newton_updates / kernel_ms may be NULL.
+ * Errors: MOFEM_E_NEWTON ("Too many iterations!", invShapeFunction.py:68), MOFEM_E_ELEMENT (the ValueError of :1021). */
+int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double *vert_xy, const int32_t *vert_elem,
+                   int64_t n_elem, const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
+                   int64_t *newton_updates, double *kernel_ms);
+
 /* Per-kernel profile of the PCG loop: when on, every iteration of mofem_solve records CUDA events around its three
  * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */

@@ -17,6 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 SOURCES = {
     "integrate.cu": ["-fmad=false"],
     "sample.cu": ["-fmad=false"],
+    "rho.cu": ["-fmad=false"],
     "csr.cu": [],
     "scan.cu": [],
     "pcg.cu": [],

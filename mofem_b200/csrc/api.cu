@@ -37,6 +37,8 @@ struct mofem_ctx {
     size_t slab_hot_bytes = 0;
     bool slab_in_xbuf = false;
     int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
+    int spmv_ring = 1;    // PCG SpMV streams the matrix through shared memory with the TMA (spmv_ring.cuh); 0: row kernel
+    int pdl = 1;          // programmatic dependent launch between the three kernels of a PCG iteration (single GPU)
     int cell_kernel = 0;  // 1: quad4 overlay cells on the warp-cooperative cell kernel (bit-identical, measured slower: 3.1 vs 2.55 ms at syn-1M)
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -272,7 +274,7 @@ int mofem_symbolic(mofem_ctx *ctx)
     C.n_node = P.n_node;
     int32_t *row_cnt, *row_uniq;
     if ((rc = dev_alloc(ctx, &row_cnt, P.n_node, tmp)) || (rc = dev_alloc(ctx, &row_uniq, P.n_node, tmp)) ||
-        (rc = dev_alloc(ctx, &C.row_start, P.n_node + 1, pool)) || (rc = dev_alloc(ctx, &C.node_ptr, P.n_node + 1, pool))) {
+        (rc = dev_alloc(ctx, &C.row_start, P.n_node + 1, pool)) || (rc = dev_alloc(ctx, &C.node_ptr, P.n_node + 4, pool))) {
         cleanup(); return rc;
     }
     CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
@@ -296,7 +298,7 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(exclusive_scan_i32_to_i64(row_uniq, C.node_ptr, P.n_node, C.node_ptr + P.n_node, s, &L));
     CKT(cudaMemcpyAsync(&C.n_upair, C.node_ptr + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
-    if ((rc = dev_alloc(ctx, &C.node_idx, C.n_upair, pool)) || (rc = dev_alloc(ctx, &C.pair_row, C.n_upair, pool)) ||
+    if ((rc = dev_alloc(ctx, &C.node_idx, C.n_upair + 8, pool)) || (rc = dev_alloc(ctx, &C.pair_row, C.n_upair, pool)) ||
         (rc = dev_alloc(ctx, &C.contrib_ptr, C.n_upair + 1, pool)) || (rc = dev_alloc(ctx, &C.contrib_src, C.n_entry, pool)) ||
         (rc = dev_alloc(ctx, &ctx->data, 4 * C.n_upair, pool)) || (rc = dev_alloc(ctx, &ctx->blk_val, 4 * ctx->n_pair, pool))) {
         cleanup(); return rc;
@@ -427,6 +429,7 @@ static DevSystem system_of(mofem_ctx *ctx)
     DevSystem A;
     A.n = 2 * ctx->P.n_node; A.node_ptr = ctx->C.node_ptr; A.node_idx = ctx->C.node_idx; A.data = ctx->data;
     A.n_own = ctx->have_halo ? 2 * ctx->dist.n_owned_node : A.n;
+    A.n_blk = ctx->C.n_upair;   // upper bound of the sub-blocks in the owned rows (exact on a single GPU)
     return A;
 }
 static const DistPlan *dist_of(mofem_ctx *ctx) { return ctx->have_halo ? &ctx->dist : nullptr; }
@@ -463,6 +466,10 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;
+        W.ring_cap = ring_tile_capacity(n / 2, ctx->C.n_upair);
+        char *tiles;
+        if ((rc = dev_alloc(ctx, &tiles, 32 * W.ring_cap, pool))) return rc;
+        W.ring_tiles = tiles;
         ctx->sys_n = n;
     }
     tic(ctx);
@@ -517,6 +524,7 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
             cudaGetLastError();
         }
     }
+    ctx->W.use_ring = ctx->spmv_ring; ctx->W.use_pdl = ctx->pdl;
     cudaError_t run_err = pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s,
                                   &ctx->launches[3], prof, ctx->prof_ms);
     if (window) {
@@ -813,6 +821,56 @@ int mofem_sample(mofem_ctx *ctx, const double *u, int32_t n_sampling, int32_t so
     return MOFEM_OK;
 }
 
+// ---- weight functions of the overlay vertices -------------------------------------
+int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double *vert_xy, const int32_t *vert_elem,
+                   int64_t n_elem, const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
+                   int64_t *newton_updates, double *kernel_ms)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    if (n_vert < 0 || n_elem < 0 || n_mesh < 1 || n_mesh > 255) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_rho_eval: bad sizes");
+    if (n_vert > 0 && (!vert_xy || !vert_elem || !rho)) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_rho_eval: null vertex array");
+    if (n_elem > 0 && (!elem_nv || !elem_xy || !elem_w)) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_rho_eval: null element array");
+    if (newton_updates) *newton_updates = 0;
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (n_vert == 0) return MOFEM_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<void *> tmp;
+    int rc;
+    const double *vxy, *exy, *ew; const int32_t *vel, *env;
+    if ((rc = upload(ctx, vert_xy, 2 * n_vert, &vxy, tmp)) || (rc = upload(ctx, vert_elem, n_vert * n_mesh, &vel, tmp)) ||
+        (rc = upload(ctx, elem_nv, n_elem, &env, tmp)) || (rc = upload(ctx, elem_xy, 8 * n_elem, &exy, tmp)) ||
+        (rc = upload(ctx, elem_w, 4 * n_elem, &ew, tmp))) { free_pool(ctx, tmp); return rc; }
+    const bool out_host = !is_device_ptr(rho);
+    double *rho_d = rho;
+    unsigned long long *nw_d;
+    int *err_d;
+    if ((out_host && (rc = dev_alloc(ctx, &rho_d, n_vert * n_mesh, tmp))) || (rc = dev_alloc(ctx, &nw_d, 1, tmp)) ||
+        (rc = dev_alloc(ctx, &err_d, 1, tmp))) { free_pool(ctx, tmp); return rc; }
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+    CKS(cudaMemsetAsync(nw_d, 0, sizeof(unsigned long long), s));
+    CKS(cudaMemsetAsync(err_d, 0, sizeof(int), s));
+    tic(ctx);
+    CKS(rho_run(n_vert, n_mesh, vxy, vel, n_elem, env, exy, ew, rho_d, err_d, nw_d, s));
+    CKS(cudaEventRecord(ctx->ev1, s));
+    int eflag = 0;
+    unsigned long long nw = 0;
+    CKS(cudaMemcpyAsync(&eflag, err_d, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKS(cudaMemcpyAsync(&nw, nw_d, sizeof(nw), cudaMemcpyDeviceToHost, s));
+    if (out_host) CKS(cudaMemcpyAsync(rho, rho_d, sizeof(double) * n_vert * n_mesh, cudaMemcpyDeviceToHost, s));
+    CKS(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CKS(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+#undef CKS
+    free_pool(ctx, tmp);
+    if (newton_updates) *newton_updates = (int64_t)nw;
+    if (kernel_ms) *kernel_ms = ms;
+    if (eflag == MOFEM_E_NEWTON) return ctx_fail(ctx, MOFEM_E_NEWTON, "Too many iterations!");
+    if (eflag == MOFEM_E_ELEMENT) return ctx_fail(ctx, MOFEM_E_ELEMENT, "rho: incident element with neither 3 nor 4 corner vertices");
+    if (eflag) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_rho_eval: element index out of range");
+    return MOFEM_OK;
+}
+
 int mofem_set_profile(mofem_ctx *ctx, int on)
 {
     if (!ctx) return MOFEM_E_ARG;
@@ -824,6 +882,8 @@ int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return MOFEM_E_ARG;
     if (!strcmp(name, "l2_persist")) { ctx->l2_persist = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "spmv_ring")) { ctx->spmv_ring = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "pdl")) { ctx->pdl = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "cell_kernel")) { ctx->cell_kernel = (int)value; return MOFEM_OK; }   // takes effect at the next mofem_symbolic
     return ctx_fail(ctx, MOFEM_E_ARG, std::string("mofem_set_option: unknown option ") + name);
 }

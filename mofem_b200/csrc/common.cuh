@@ -102,6 +102,11 @@ cudaError_t sample_fill_units(const DevProblem &p, const int64_t *unit_off, int3
 cudaError_t sample_run(const DevProblem &p, const int32_t *unit_cell, const int64_t *unit_tri, int64_t n_unit, int nS,
                        const double *grid, const double *u, double *out, int *err, cudaStream_t s);
 
+// rho.cu
+cudaError_t rho_run(int64_t n_vert, int n_mesh, const double *vert_xy, const int32_t *vert_elem, int64_t n_elem,
+                    const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho, int *err,
+                    unsigned long long *newton_total, cudaStream_t s);
+
 // pcg.cu
 struct DevSystem {
     int64_t n;            // local scalar unknowns (2 * local nodes, ghosts included)
@@ -109,6 +114,7 @@ struct DevSystem {
     const int64_t *node_ptr;
     const int32_t *node_idx;
     const double *data;   // scalar CSR values
+    int64_t n_blk = 0;    // 2x2 sub-blocks stored in the rows of this rank (node_ptr[n_own / 2])
 };
 
 // Row-partitioned operation: local node order is [owned | ghosts grouped by owner rank].
@@ -168,8 +174,15 @@ struct PcgBuffers {
     double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
     double *sc;                                // 8 scalars
     uint8_t *row_halo;                         // [local nodes] 1 = row references a ghost column (peer path)
-    unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = peer time-out flag
+    unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = peer time-out flag,
+                                               // [7] = largest node-row degree (written by pcg_setup)
+    // TMA-ring SpMV (spmv_ring.cuh): tile table built by pcg_setup; capacity in tiles
+    void *ring_tiles = nullptr;
+    int64_t ring_cap = 0;
+    int n_tile = 0;
+    int use_ring = 1, use_pdl = 1;             // tuning switches (mofem_set_option)
 };
+int64_t ring_tile_capacity(int64_t n_node, int64_t n_blk);
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
                       PcgBuffers &w, const DistPlan *dist, cudaStream_t s, int64_t *launches);
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist, double rtol, int maxit,

@@ -15,6 +15,7 @@
 // last block to finish sums the partials in index order and publishes the scalar.  alpha/beta live on the
 // device; the host only polls the residual every PCG_CHUNK iterations.
 #include "common.cuh"
+#include "spmv_ring.cuh"
 
 namespace mofem {
 
@@ -195,6 +196,7 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
        const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp, const double *done_flag)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
+    ring::grid_dep_wait();   // PDL: no-op unless launched with the programmatic-serialization attribute
     if (DOT && done_flag && *done_flag != 0.0) return;
     if (P2P && blockIdx.x == 0 && hp.n_nb) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
@@ -256,6 +258,7 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
             }
         }
     }
+    ring::grid_dep_launch();   // the dependent (update kernel) may become resident from here on
     if (DOT) {
         const double s = block_sum(dot, sm);
         double total;
@@ -264,6 +267,66 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
             else if (threadIdx.x == 0) *dot_out = total;
         }
     }
+}
+
+// ---- TMA-ring SpMV of the single-GPU PCG loop (spmv_ring.cuh) -------------------------------------------------------
+// 2 CTAs per SM, 12 consumer warps + 1 producer warp each, 2 stages of <= 960 rows + sub-blocks (tuned with
+// tools/spmv_lab2.cu inside a PCG-shaped loop: 85 us against 97 us for the row kernel on the 1 M-cell bench matrix).
+using PcgRing = RingCfg<960, 128, 2, 12>;
+constexpr int RING_GRID = 148 * 2;
+static_assert(RING_GRID <= PCG_MAX_PART, "partials buffer too small");
+
+int64_t ring_tile_capacity(int64_t n_node, int64_t n_blk) { return (n_node + n_blk) / PcgRing::SPAN + 2; }
+
+// tile t = node rows a with  t*SPAN <= a + node_ptr[a] < (t+1)*SPAN  (the key grows by 1 + degree per row, so a tile
+// holds <= SPAN rows and < SPAN + maxdeg sub-blocks); one thread per tile, two binary searches
+__global__ void k_ring_tiles(int64_t n_node, const int64_t *__restrict__ node_ptr, int n_tile, RingTile *__restrict__ tiles)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tile) return;
+    auto first_row_with_key_ge = [&](int64_t key) {
+        int64_t lo = 0, hi = n_node;          // answer in [0, n_node]
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (mid + node_ptr[mid] >= key) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    const int64_t a0 = first_row_with_key_ge((int64_t)t * PcgRing::SPAN), a1 = first_row_with_key_ge((int64_t)(t + 1) * PcgRing::SPAN);
+    RingTile rt;
+    rt.a0 = (int32_t)a0; rt.a1 = (int32_t)a1; rt.b0 = node_ptr[a0]; rt.b1 = node_ptr[a1]; rt._pad = 0;
+    tiles[t] = rt;
+}
+
+// q = K p and the partial of p.q; launched with the PDL attribute the producer warp fills the ring while the direction
+// kernel of the previous iteration is still draining (the matrix does not depend on it)
+__global__ void __launch_bounds__(PcgRing::THREADS, 2)
+k_spmv_ring(int n_tile, const RingTile *__restrict__ tiles, const int64_t *__restrict__ node_ptr,
+            const int32_t *__restrict__ node_idx, const double *__restrict__ data, const double *__restrict__ x,
+            double *__restrict__ y, const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter,
+            double *dot_out)
+{
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ double sm[32];
+    double dot = 0.0;
+    ring_spmv_body<PcgRing, true, true>(ring_smem, n_tile, tiles, node_ptr, node_idx, data, x, y, fixed, dot);
+    const double s = block_sum(dot, sm);
+    double total;
+    if (grid_sum(s, part_dot, counter, sm, total) && threadIdx.x == 0) *dot_out = total;
+}
+
+// kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start while its
+// predecessor in the stream drains; it orders itself with griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(bool pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 // rows of the local matrix that reference a ghost column (peer path: they are multiplied after the halo has arrived)
@@ -279,9 +342,14 @@ __global__ void k_mark_halo_rows(int64_t n_node, const int64_t *__restrict__ nod
 
 // diagonal -> inverse (0 on fixed or empty rows)
 __global__ void k_diag_inv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
-                           const double *__restrict__ data, const uint8_t *__restrict__ fixed, double *__restrict__ dinv)
+                           const double *__restrict__ data, const uint8_t *__restrict__ fixed, double *__restrict__ dinv,
+                           unsigned int *max_deg)
 {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int dg = a < n_node ? (unsigned int)(node_ptr[a + 1] - node_ptr[a]) : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) dg = max(dg, __shfl_xor_sync(0xffffffffu, dg, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_deg, dg);
     if (a >= n_node) return;
     const int64_t r0 = node_ptr[a], deg = node_ptr[a + 1] - r0;
     double dx = 0.0, dy = 0.0;
@@ -364,6 +432,8 @@ k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restr
              double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp, double *out2)
 {
     __shared__ double sm[VEC_BLOCK / 32];
+    ring::grid_dep_wait();        // PDL: no-ops unless launched with the programmatic-serialization attribute
+    ring::grid_dep_launch();
     if (out2 == nullptr || out2 != sc + sc_rz(it + 1)) {   // row-partitioned runs poll rarely and rely on the stop flag
         if (sc[SC_DONE] != 0.0) return;
     }
@@ -398,6 +468,8 @@ __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
                 const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, double tol2, unsigned int *done_counter)
 {
+    ring::grid_dep_wait();
+    ring::grid_dep_launch();
     if (done_counter && sc[SC_DONE] != 0.0) return;
     double rz_new, rr;
     if (P2P) {
@@ -548,9 +620,20 @@ cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed,
     if (e != cudaSuccess) return e;
     if (n_own) {
         k_build_rhs<<<(unsigned)((n_own + 255) / 256), 256, 0, s>>>(n_own, fixed, f, w.q, w.b);
-        k_diag_inv<<<(unsigned)((n_own / 2 + 255) / 256), 256, 0, s>>>(n_own / 2, A.node_ptr, A.node_idx, A.data, fixed, w.dinv);
+        k_diag_inv<<<(unsigned)((n_own / 2 + 255) / 256), 256, 0, s>>>(n_own / 2, A.node_ptr, A.node_idx, A.data, fixed, w.dinv,
+                                                                        w.counters + 7);
     }
     if (launches) *launches += 4;
+    // tile table of the TMA-ring SpMV (single GPU; the row-partitioned paths keep the row kernel)
+    w.n_tile = 0;
+    if (!(dist && dist->world > 1) && n_own && w.ring_tiles) {
+        const int64_t nt = (n_own / 2 + A.n_blk + PcgRing::SPAN - 1) / PcgRing::SPAN;
+        if (nt <= w.ring_cap && nt < (int64_t)1 << 30) {
+            w.n_tile = (int)nt;
+            k_ring_tiles<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(n_own / 2, A.node_ptr, w.n_tile, reinterpret_cast<RingTile *>(w.ring_tiles));
+            if (launches) ++*launches;
+        }
+    }
     return cudaGetLastError();
 }
 
@@ -666,13 +749,48 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     const int n_nb = dist ? (int)dist->nb_rank.size() : 0;
     const int64_t n_send = dist && !dist->send_ptr.empty() ? dist->send_ptr.back() : 0;
     if (!(dist && dist->world > 1) && chunk > 50) chunk = 50;   // a single GPU polls cheaply: no stop flag, short chunks
+    // single GPU: TMA-ring SpMV (if every node row fits a ring stage) and programmatic dependent launch between the kernels
+    const bool single = !(dist && dist->world > 1);
+    bool ring_on = false;
+    if (single && w.use_ring && w.n_tile > 0) {
+        unsigned int max_deg = 0;
+        if ((e = cudaMemcpyAsync(&max_deg, w.counters + 7, sizeof(unsigned int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        ring_on = max_deg <= (unsigned int)PcgRing::MAXDEG;
+        if (ring_on) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                if ((e = cudaFuncSetAttribute(k_spmv_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
+                attr_set = true;
+            }
+        }
+    }
+    const bool pdl = single && w.use_pdl && !prof && ring_on;   // measured: PDL costs time with the row kernel (181 vs 133 us per iteration)
+    const int g_ring = w.n_tile < RING_GRID ? w.n_tile : RING_GRID;
     while (it < maxit) {
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
         cudaEvent_t *ev = prof ? prof + (size_t)pool * 4 * chunk : nullptr;
         for (int k = 0; k < todo; k++, it++) {
             if (ev) cudaEventRecord(ev[4 * k], s);
-            if (!peer) {
+            if (single) {
+                if (ring_on)
+                    e = launch_ex(pdl, k_spmv_ring, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile,
+                                  reinterpret_cast<const RingTile *>(w.ring_tiles), A.node_ptr, A.node_idx, A.data, (const double *)w.p, w.q,
+                                  fixed, w.part_c, w.counters, w.sc + SC_PQ);
+                else
+                    e = launch_ex(pdl, k_spmv<true, false>, gs, SPMV_BLOCK, 0, s, n_node, A.node_ptr, A.node_idx, A.data, (const double *)w.p,
+                                  w.q, fixed, w.part_c, w.counters, w.sc + SC_PQ, NO_P2P, 0, (const int *)nullptr, (const uint8_t *)nullptr,
+                                  (const int32_t *)nullptr, (int64_t)0, HaloPush{}, (const double *)nullptr);
+                if (e != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                if ((e = launch_ex(pdl, k_pcg_update<false>, gv, VEC_BLOCK, 0, s, n2, it, w.sc, (const double2 *)p2, (const double2 *)q2, dinv2, x2, r2,
+                                   w.part_a, w.part_b, w.counters + 1, NO_P2P, w.sc + sc_rz(it + 1))) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 2], s);
+                if ((e = launch_ex(pdl, k_pcg_direction<false>, gv, VEC_BLOCK, 0, s, n2, it, w.sc, (const double2 *)r2, dinv2, p2, NO_P2P, tol2,
+                                   (unsigned int *)nullptr)) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 3], s);
+            } else if (!peer) {
                 if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
                 const bool multi = dist && dist->world > 1;   // NCCL: partials are all-reduced INTO the global slots
                 launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + (multi ? SC_PART_PQ : SC_PQ), s,

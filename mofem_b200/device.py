@@ -224,6 +224,22 @@ class Context:
                                       int(nu.value), C.byref(nu)))
         return out
 
+    def rho_eval(self, vert_xy, vert_elem, elem_nv, elem_xy, elem_w, out=None):
+        """Weight functions of overlay vertices (``mofem_rho_eval``): rho [V, M].  Inputs may be numpy arrays or device
+        tensors; ``out`` (optional) a preallocated [V, M] array / device tensor.  Returns (rho, newton updates, kernel ms)."""
+        if isinstance(vert_elem, np.ndarray):
+            vert_xy = _c(vert_xy, np.float64); vert_elem = _c(vert_elem, np.int32); elem_nv = _c(elem_nv, np.int32)
+            elem_xy = _c(elem_xy, np.float64); elem_w = _c(elem_w, np.float64)
+        V, M = int(vert_elem.shape[0]), int(vert_elem.shape[1])
+        if out is None:
+            out = np.empty((V, M))
+        nw = C.c_int64(0)
+        ms = C.c_double(0)
+        self._ck(self._L.mofem_rho_eval(self._h, V, M, _lib.ptr(vert_xy), _lib.ptr(vert_elem), int(elem_nv.shape[0]),
+                                        _lib.ptr(elem_nv), _lib.ptr(elem_xy), _lib.ptr(elem_w), _lib.ptr(out),
+                                        C.byref(nw), C.byref(ms)))
+        return out, int(nw.value), float(ms.value)
+
     def set_option(self, name: str, value: int):
         self._ck(self._L.mofem_set_option(self._h, name.encode(), int(value)))
         return self

@@ -931,3 +931,56 @@ int64_t orc_coo_tocsr(int64_t n_row, int64_t nnz, const int64_t *I, const int64_
     free(cnt); free(tmp); free(cur);
     return out;
 }
+
+/* ------------------------------------------------------------------ */
+/* weight functions                                   */
+/* ------------------------------------------------------------------ */
+
+/* np.inner of two 1-D float64 arrays = cblas_ddot (OpenBLAS): n < 32 runs the scalar tail loop
+ * dot += y[i]*x[i], compiled with contraction -> fma chain starting from 0. */
+static double np_inner(const double *a, const double *b, int n)
+{
+    double dot = 0.0;
+    for (int i = 0; i < n; i++) dot = fma(b[i], a[i], dot);
+    return dot;
+}
+
+/* planeSweepMeshes.rhoCalculation:991-1030, per overlay vertex.  vert_elem[v][m] = incident element of the mesh
+ * slot m (-1 = none) of the face that first visits the vertex; elements carry their 3 or 4 corner vertices
+ * (element.vertex) and corner weights.  rho[v][m]: weight of mesh m (slots >= 1 multiplied by 9, :1024-1025),
+ * normalised by Python's left-to-right sum (:1027).  Returns 0, -1 "Too many iterations!", -2 ValueError (:1021). */
+int orc_rho_eval(int64_t n_vert, int32_t n_mesh, const double *vert_xy, const int32_t *vert_elem,
+                 const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
+                 int64_t *newton_total)
+{
+    int64_t nw = 0;
+    for (int64_t v = 0; v < n_vert; v++) {
+        double *r = rho + v * n_mesh;
+        const double *xy = vert_xy + 2 * v;
+        for (int m = 0; m < n_mesh; m++) {
+            r[m] = 0.0;
+            int32_t e = vert_elem[v * n_mesh + m];
+            if (e < 0) continue;
+            const double *c = elem_xy + 8 * (int64_t)e, *w = elem_w + 4 * (int64_t)e;
+            if (elem_nv[e] == 4) {
+                double iso[2], N[4], dN[8];
+                int it = orc_inv_newton(c, 4, xy, iso);
+                if (it < 0) return -1;
+                nw += it;
+                quad_N_dN(iso[0], iso[1], N, dN);
+                r[m] = np_inner(N, w, 4);
+            } else if (elem_nv[e] == 3) {
+                double iso[3];
+                orc_inv_tri(c, xy, iso);
+                r[m] = np_inner(iso, w, 3);
+            } else
+                return -2;
+        }
+        for (int m = 1; m < n_mesh; m++) r[m] *= 9;
+        double s = 0.0;
+        for (int m = 0; m < n_mesh; m++) s += r[m];
+        for (int m = 0; m < n_mesh; m++) r[m] /= s;
+    }
+    if (newton_total) *newton_total = nw;
+    return 0;
+}

@@ -45,6 +45,11 @@ int orc_assemble_coo(const orc_problem *p, int64_t *I, int64_t *J, double *V, in
 int64_t orc_coo_tocsr(int64_t n_row, int64_t nnz, const int64_t *I, const int64_t *J, const double *V,
                       int64_t *indptr, int64_t *indices, double *data);
 
+/* planeSweepMeshes.rhoCalculation:991-1030 on flat arrays (see mofem_oracle.c). */
+int orc_rho_eval(int64_t n_vert, int32_t n_mesh, const double *vert_xy, const int32_t *vert_elem,
+                 const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
+                 int64_t *newton_total);
+
 #ifdef __cplusplus
 }
 #endif

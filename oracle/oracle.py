@@ -61,6 +61,8 @@ def lib():
         L.orc_gauss_quad.argtypes = [C.c_int, c_d_p, c_d_p]
         L.orc_material_matrix.argtypes = [C.c_double, C.c_double, C.c_int, c_d_p]
         L.orc_amore_nint.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.orc_rho_eval.restype = C.c_int
+        L.orc_rho_eval.argtypes = [C.c_int64, C.c_int32, c_d_p, c_i32_p, c_i32_p, c_d_p, c_d_p, c_d_p, c_i64_p]
         _LIB = L
     return _LIB
 
@@ -190,3 +192,20 @@ def material_matrix(E, nu, problem_type):
     if lib().orc_material_matrix(float(E), float(nu), int(problem_type), _p(D, c_d_p)):
         raise ValueError("No such a problem type!")
     return D
+
+
+def rho_eval(vert_xy, vert_elem, elem_nv, elem_xy, elem_w):
+    """planeSweepMeshes.rhoCalculation:991-1030 on flat arrays -> (rho [V,M], newton updates)."""
+    vert_xy = _d(vert_xy); vert_elem = np.ascontiguousarray(vert_elem, np.int32)
+    elem_nv = np.ascontiguousarray(elem_nv, np.int32); elem_xy = _d(elem_xy); elem_w = _d(elem_w)
+    V, M = vert_elem.shape
+    rho = np.empty((V, M))
+    nw = C.c_int64(0)
+    with np.errstate(all="ignore"):
+        rc = lib().orc_rho_eval(V, M, _p(vert_xy, c_d_p), _p(vert_elem, c_i32_p), _p(elem_nv, c_i32_p),
+                                _p(elem_xy, c_d_p), _p(elem_w, c_d_p), _p(rho, c_d_p), C.byref(nw))
+    if rc == -1:
+        raise AssertionError("Too many iterations!")
+    if rc == -2:
+        raise ValueError
+    return rho, nw.value

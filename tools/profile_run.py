@@ -1,9 +1,10 @@
-"""Short run of every kernel of the hot path at the bench workload, for ncu (a few PCG iterations only).
+"""Assemble + a fixed number of PCG iterations on the bench problem, for ncu / tuning runs (development tool).
 
-    python tools/profile_run.py [n0] [pcg_iterations]
+    python tools/profile_run.py [n0=664] [iters=20] [key=value ...]     keys: l2_persist, spmv_ring, pdl, profile, reps
 """
 import os
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,9 +14,10 @@ from mofem_b200.device import Context
 from mofem_b200.flatten import FlatProblem
 from mofem_b200.overlay_gen import patch_family
 
-n0 = int(sys.argv[1]) if len(sys.argv) > 1 else 664
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-l2 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+pos = [a for a in sys.argv[1:] if "=" not in a]
+kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+n0 = int(pos[0]) if len(pos) > 0 else 664
+iters = int(pos[1]) if len(pos) > 1 else 20
 fp, rhs, fixed, val = patch_family(n0)
 dev = torch.device("cuda", 0)
 for k in FlatProblem.ARRAYS:
@@ -23,12 +25,34 @@ for k in FlatProblem.ARRAYS:
     if a is not None and k != "elem_mesh":
         setattr(fp, k, torch.from_numpy(np.ascontiguousarray(a)).to(dev))
 ctx = Context(0)
-ctx.set_option("l2_persist", l2)
-ctx.set_profile(True)
-for rep in range(2):
-    ctx.set_problem(fp).symbolic().assemble()
-    ctx.set_system(torch.from_numpy(rhs).to(dev), torch.from_numpy(fixed).to(dev), torch.from_numpy(val).to(dev))
-    u, info = ctx.solve(rtol=1e-10, maxit=iters, check=False)
-pp = ctx.pcg_profile()
-print("per-iteration us:", {k: round(v / max(pp["iterations"], 1) * 1e3, 1) for k, v in pp.items() if k != "iterations"}, "l2_persist", l2)
-print("ok", ctx.info(), info, ctx.timing())
+ctx.set_problem(fp).symbolic().assemble()
+ctx.set_system(torch.from_numpy(rhs).to(dev), torch.from_numpy(fixed).to(dev), torch.from_numpy(val).to(dev))
+configs = kv.get("configs")
+runs = []
+if configs:      # e.g. configs=ring:pdl,ring,pdl,none   (each: the switches that are ON)
+    for c in configs.split(","):
+        on = set(c.split(":"))
+        runs.append(dict(spmv_ring=int("ring" in on), pdl=int("pdl" in on), l2_persist=int("nol2" not in on), profile=int("prof" in on)))
+else:
+    runs.append(dict(spmv_ring=int(kv.get("spmv_ring", 1)), pdl=int(kv.get("pdl", 1)), l2_persist=int(kv.get("l2_persist", 1)),
+                     profile=int(kv.get("profile", 0))))
+for opt in runs:
+    for k in ("spmv_ring", "pdl", "l2_persist"):
+        ctx.set_option(k, opt[k])
+    ctx.set_profile(bool(opt["profile"]))
+    best = None
+    for rep in range(int(kv.get("reps", 3))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        u, info = ctx.solve(rtol=1e-10, maxit=iters, check=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ms = ctx.timing()["solve_ms"]
+        best = ms if best is None else min(best, ms)
+    line = {"opt": opt, "iterations": info["iterations"], "solve_ms": round(best, 3), "us_per_iteration": round(best / max(info["iterations"], 1) * 1e3, 2),
+            "relres_rec": info["relres_rec"], "relres_true": info["relres_true"]}
+    if opt["profile"]:
+        pp = ctx.pcg_profile()
+        line["kernel_us"] = {k: round(v / max(pp["iterations"], 1) * 1e3, 2) for k, v in pp.items() if k != "iterations"}
+    print(line, flush=True)
+print("ok", ctx.info())
