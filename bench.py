@@ -119,6 +119,7 @@ def algorithmic_bytes(info, n_dof):
         "spmv_scalar_csr": 12 * nnz + 4 * (n_dof + 1) + 16 * n_dof,
         "update": 8 * n_dof * 7,         # reads p, q, x, r, dinv; writes x, r
         "direction": 8 * n_dof * 4,      # reads r, dinv, p; writes p
+        "fused": 8 * n_dof * 8,          # single GPU, one kernel: reads q, r, dinv, p, x; writes r, x, p
         # numeric reduce: every block value once (32 B per node pair), its 4 B source slot, CSR values out
         "numeric": 32 * n_pair + 4 * n_contrib + 8 * nnz,
     }
@@ -199,6 +200,9 @@ def main():
     ap.add_argument("--ref-n0", type=int, default=256, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events inside the PCG loop")
+    ap.add_argument("--profile-every", type=int, default=16,
+                    help="record CUDA events around the PCG kernels of every N-th iteration of the timed steps (1 = all; the "
+                         "sampled iterations lose their launch overlap, so N = 1 costs ~10 %% of the step)")
     ap.add_argument("--l2-persist", type=int, default=1, help="pin the PCG vectors in L2 (library default: 1)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
@@ -292,7 +296,7 @@ def main():
     ctx = Context(local)
     if world > 1:
         init_comm(ctx)
-    ctx.set_profile(not args.no_profile)
+    ctx.set_profile(0 if args.no_profile else max(1, args.profile_every))
     ctx.set_option("l2_persist", args.l2_persist)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     maxit = 400000
@@ -390,18 +394,27 @@ def main():
             traffic = json.load(f)["dram_bytes_per_launch"]
     if spmv_ms:
         ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
-        roofline = {"kernel": "k_spmv (block-CSR SpMV inside Jacobi-PCG)", "bound": "hbm", "achieved": ach,
+        ring = world == 1
+        roofline = {"kernel": ("k_spmv_ring (block-CSR SpMV of the Jacobi-PCG loop, matrix streamed through shared memory by TMA)" if ring
+                               else "k_spmv (block-CSR SpMV inside Jacobi-PCG, row kernel with in-kernel halo exchange)"),
+                    "bound": "hbm", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                     "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
                     "algorithmic_bytes_per_launch": ab["spmv"], "avg_launch_ms": spmv_ms,
                     "scalar_csr_equivalent_gbs": ab["spmv_scalar_csr"] / (spmv_ms * 1e-3) / 1e9,
-                    "share_of_step": prof["spmv_ms"] / args.steps / step_ms}
+                    "share_of_step": spmv_ms * si["iterations"] / step_ms,
+                    "launches_timed": prof["iterations"], "sampled_every": (0 if args.no_profile else max(1, args.profile_every))}
     kernels = {}
     if prof["iterations"]:
-        for name in ("update", "direction"):
-            ms = prof[name + "_ms"] / iters
-            kernels["k_pcg_" + name] = {"avg_launch_ms": ms, "gbs": ab[name] / (ms * 1e-3) / 1e9,
-                                        "frac_hbm": ab[name] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if world == 1:      # update + direction run as one kernel (grid barrier in between)
+            ms = (prof["update_ms"] + prof["direction_ms"]) / iters
+            kernels["k_pcg_fused"] = {"avg_launch_ms": ms, "gbs": ab["fused"] / (ms * 1e-3) / 1e9,
+                                      "frac_hbm": ab["fused"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        else:
+            for name in ("update", "direction"):
+                ms = prof[name + "_ms"] / iters
+                kernels["k_pcg_" + name] = {"avg_launch_ms": ms, "gbs": ab[name] / (ms * 1e-3) / 1e9,
+                                            "frac_hbm": ab[name] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     nm = phases["numeric_ms"] / args.steps
     kernels["k_numeric"] = {"avg_launch_ms": nm, "gbs": ab["numeric"] / (nm * 1e-3) / 1e9,
                             "frac_hbm": ab["numeric"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"]}

@@ -181,8 +181,8 @@ int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double 
                    int64_t n_elem, const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
                    int64_t *newton_updates, double *kernel_ms);
 
-/* Per-kernel profile of the PCG loop: when on, every iteration of mofem_solve records CUDA events around its three
- * kernels on the context's stream.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
+/* Per-kernel profile of the PCG loop: on = 1 records CUDA events around the kernels of every iteration of mofem_solve on the
+ * context's stream, on = N > 1 around those of every N-th iteration (the others keep their launch overlap), 0 = off.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */
 int mofem_set_profile(mofem_ctx *ctx, int on);
 /* Tuning switches: "l2_persist" (default 1) pins the PCG vectors in L2 during mofem_solve; "cell_kernel" (default 0)

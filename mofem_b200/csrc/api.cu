@@ -34,10 +34,12 @@ struct mofem_ctx {
     std::vector<void *> sys_allocs;
     int64_t sys_n = 0;
     double *slab = nullptr;
-    size_t slab_hot_bytes = 0;
+    size_t slab_hot_bytes = 0, slab_vec_bytes = 0;
+    int l2_window = 5;    // leading vectors of the slab (p, r, dinv, q, x) inside the L2 persistence window
     bool slab_in_xbuf = false;
     int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
     int spmv_ring = 1;    // PCG SpMV streams the matrix through shared memory with the TMA (spmv_ring.cuh); 0: row kernel
+    int fused_vec = 1;    // update + direction of a PCG iteration as one kernel with a grid barrier (single GPU)
     int pdl = 1;          // programmatic dependent launch between the three kernels of a PCG iteration (single GPU)
     int cell_kernel = 0;  // 1: quad4 overlay cells on the warp-cooperative cell kernel (bit-identical, measured slower: 3.1 vs 2.55 ms at syn-1M)
     // timing
@@ -49,7 +51,7 @@ struct mofem_ctx {
     DistPlan dist;
     bool have_halo = false;
     std::vector<void *> dist_allocs;
-    bool profile = false;
+    int profile = 0;      // 0 off, 1 events around the kernels of every PCG iteration, N > 1 of every N-th iteration
     std::vector<cudaEvent_t> prof_events;
     double prof_ms[4]{};
 };
@@ -457,9 +459,11 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
             slab = ctx->dist.xbuf + p2p_p_off(ctx->dist.world);
         } else if ((rc = dev_alloc(ctx, &slab, 7 * npad, pool))) return rc;
         ctx->slab_in_xbuf = want_xbuf;
-        W.p = slab; W.q = slab + npad; W.x = slab + 2 * npad; W.r = slab + 3 * npad; W.dinv = slab + 4 * npad;
+        // order = how much a vector gains from staying in L2: p (gathered by the SpMV, read by both vector kernels), r and dinv
+        // (both vector kernels), then q and x (one kernel each); "l2_window" picks how many of them the window covers
+        W.p = slab; W.r = slab + npad; W.dinv = slab + 2 * npad; W.q = slab + 3 * npad; W.x = slab + 4 * npad;
         W.b = slab + 5 * npad; W.ufix = slab + 6 * npad;
-        ctx->slab = slab; ctx->slab_hot_bytes = sizeof(double) * (size_t)(5 * npad);
+        ctx->slab = slab; ctx->slab_vec_bytes = sizeof(double) * (size_t)npad; ctx->slab_hot_bytes = 5 * ctx->slab_vec_bytes;
         if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
             (rc = dev_alloc(ctx, &W.sc, 16, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
@@ -512,11 +516,12 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
     if (ctx->l2_persist && ctx->slab_hot_bytes) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-            const size_t want = std::min<size_t>(ctx->slab_hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            const size_t hot = std::min<size_t>(ctx->slab_hot_bytes, ctx->slab_vec_bytes * (size_t)std::max(1, std::min(5, ctx->l2_window)));
+            const size_t want = std::min<size_t>(hot, (size_t)prop.persistingL2CacheMaxSize);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
             cudaStreamAttrValue attr{};
             attr.accessPolicyWindow.base_ptr = ctx->slab;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->slab_hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot, (size_t)prop.accessPolicyMaxWindowSize);
             attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -524,9 +529,9 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
             cudaGetLastError();
         }
     }
-    ctx->W.use_ring = ctx->spmv_ring; ctx->W.use_pdl = ctx->pdl;
+    ctx->W.use_ring = ctx->spmv_ring; ctx->W.use_pdl = ctx->pdl; ctx->W.use_fused = ctx->fused_vec;
     cudaError_t run_err = pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s,
-                                  &ctx->launches[3], prof, ctx->prof_ms);
+                                  &ctx->launches[3], prof, ctx->prof_ms, ctx->profile);
     if (window) {
         cudaStreamAttrValue attr{};
         attr.accessPolicyWindow.num_bytes = 0;
@@ -655,7 +660,7 @@ static void p2p_close(mofem_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->slab_in_xbuf) {   // the PCG vectors lived in the exchange buffer: the system has to be set again
         free_pool(ctx, ctx->sys_allocs);
-        ctx->sys_n = 0; ctx->slab_in_xbuf = false; ctx->slab = nullptr; ctx->slab_hot_bytes = 0;
+        ctx->sys_n = 0; ctx->slab_in_xbuf = false; ctx->slab = nullptr; ctx->slab_hot_bytes = 0; ctx->slab_vec_bytes = 0;
         ctx->have_system = ctx->have_solution = false;
     }
     for (int r = 0; r < (int)D.peer_host.size(); r++)
@@ -874,7 +879,7 @@ int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double 
 int mofem_set_profile(mofem_ctx *ctx, int on)
 {
     if (!ctx) return MOFEM_E_ARG;
-    ctx->profile = on != 0;
+    ctx->profile = on < 0 ? 0 : on;
     return MOFEM_OK;
 }
 
@@ -882,7 +887,9 @@ int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return MOFEM_E_ARG;
     if (!strcmp(name, "l2_persist")) { ctx->l2_persist = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "l2_window")) { ctx->l2_window = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "spmv_ring")) { ctx->spmv_ring = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "fused_vec")) { ctx->fused_vec = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "cell_kernel")) { ctx->cell_kernel = (int)value; return MOFEM_OK; }   // takes effect at the next mofem_symbolic
     return ctx_fail(ctx, MOFEM_E_ARG, std::string("mofem_set_option: unknown option ") + name);

@@ -147,7 +147,7 @@ struct DistPlan {
 // Exchange-buffer layout (doubles), identical on every rank (world = W):
 //   mailbox  [site 0..1][parity 0..1][src rank][4 x u64] = {stamp32 | 32 payload bits} x 4 (two doubles)   16 W words
 //   hflag    [parity 0..1][src rank]                                          2 W doubles
-//   slab     p, q, x, r, dinv, b, ufix -- the PCG vectors live HERE on the peer path (p first: [owned | ghost nodes][2]),
+//   slab     p, r, dinv, q, x, b, ufix -- the PCG vectors live HERE on the peer path (p first: [owned | ghost nodes][2]),
 //            so that neighbours write their boundary entries straight into the ghost segment of p and the SpMV gathers
 //            from one contiguous vector
 struct P2PDev {
@@ -175,18 +175,19 @@ struct PcgBuffers {
     double *sc;                                // 8 scalars
     uint8_t *row_halo;                         // [local nodes] 1 = row references a ghost column (peer path)
     unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = peer time-out flag,
-                                               // [7] = largest node-row degree (written by pcg_setup)
+                                               // [4] = grid barrier of the fused vector kernel, [7] = largest node-row degree (written by pcg_setup)
     // TMA-ring SpMV (spmv_ring.cuh): tile table built by pcg_setup; capacity in tiles
     void *ring_tiles = nullptr;
     int64_t ring_cap = 0;
     int n_tile = 0;
-    int use_ring = 1, use_pdl = 1;             // tuning switches (mofem_set_option)
+    int use_ring = 1, use_pdl = 1, use_fused = 1;   // tuning switches (mofem_set_option)
 };
 int64_t ring_tile_capacity(int64_t n_node, int64_t n_blk);
 cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed, const double *fixed_val,
                       PcgBuffers &w, const DistPlan *dist, cudaStream_t s, int64_t *launches);
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, const DistPlan *dist, double rtol, int maxit,
-                    int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms);
+                    int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms,
+                    int prof_every);
 cudaError_t pcg_finish(const DevSystem &A, PcgBuffers &w, const DistPlan *dist, double *u_dev, cudaStream_t s);
 cudaError_t energy_of(const DevSystem &A, const double *u, PcgBuffers &w, const DistPlan *dist, double *out_dev, cudaStream_t s);
 

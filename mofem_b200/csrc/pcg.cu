@@ -14,6 +14,8 @@
 // Dot products are two-stage with a fixed reduction order (bit-reproducible): every block writes a partial, the
 // last block to finish sums the partials in index order and publishes the scalar.  alpha/beta live on the
 // device; the host only polls the residual every PCG_CHUNK iterations.
+#include <algorithm>
+
 #include "common.cuh"
 #include "spmv_ring.cuh"
 
@@ -500,6 +502,84 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
     }
 }
 
+// ---- single GPU: update and direction in ONE kernel -------------------------------------------------------------------
+//   phase 1   r -= alpha q ; z = dinv r ; partials of r.z and r.r                 (alpha = rz / p.q)
+//   grid barrier (all CTAs are co-resident: the grid is sized by the occupancy query); every CTA then sums the partials in
+//   index order -- the same bits everywhere, no "last block" tail
+//   phase 2   x += alpha p ; p = z + beta p                                       (beta = rz_new / rz)
+// z of the first FUSE_EPT elements of a thread stays in registers across the barrier, so every vector is read once per
+// iteration (q r dinv | p x in, r | x p out: 88 MB instead of 121 MB at the 1 M-cell bench size) and one launch goes away.
+constexpr int FUSE_BLOCK = 256, FUSE_EPT = 5, FUSE_BPS = 4;
+__global__ void __launch_bounds__(FUSE_BLOCK, FUSE_BPS)
+k_pcg_fused(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, const double2 *__restrict__ q,
+            const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r, double *__restrict__ part_rz,
+            double *__restrict__ part_rr, unsigned int *barrier, unsigned int target, int *err)
+{
+    __shared__ double sm[FUSE_BLOCK / 32];
+    ring::grid_dep_wait();
+    const double pq = sc[SC_PQ], rz_old = sc[sc_rz(it)];
+    const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    double2 zc[FUSE_EPT];
+    double rz = 0.0, rr = 0.0;
+    auto residual = [&](int64_t i) {
+        const double2 qi = q[i], di = dinv[i];
+        double2 ri = r[i];
+        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
+        r[i] = ri;
+        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
+        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
+        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
+        return z;
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {
+        const int64_t i = tid + e * nth;
+        if (i < n2) zc[e] = residual(i);
+    }
+    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) residual(i);
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    // grid barrier: monotonically increasing arrival counter (zeroed by the host), one arrival per CTA
+    if (threadIdx.x == 0) {
+        part_rz[blockIdx.x] = s1; part_rr[blockIdx.x] = s2;
+        __threadfence();
+        atomicAdd(barrier, 1u);
+        long long t0 = 0;
+        for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int *>(barrier) < target; spins++) {
+            if ((spins & 0xffff) == 0xffff) {      // a CTA that never became resident: give up after ~20 s instead of hanging
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 40000000000ll) { *err = 1; break; }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    double a = 0.0, c = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) { a += __ldcg(part_rz + j); c += __ldcg(part_rr + j); }
+    const double rz_new = block_sum(a, sm), rr_new = block_sum(c, sm);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr_new; }
+    ring::grid_dep_launch();      // the next SpMV may become resident from here on (its producer warp pre-fills the ring)
+    const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    auto advance = [&](int64_t i, double2 z) {
+        const double2 pi = p[i];
+        double2 xi = x[i];
+        xi.x = fma(alpha, pi.x, xi.x); xi.y = fma(alpha, pi.y, xi.y);
+        x[i] = xi;
+        p[i] = make_double2(fma(beta, pi.x, z.x), fma(beta, pi.y, z.y));
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {
+        const int64_t i = tid + e * nth;
+        if (i < n2) advance(i, zc[e]);
+    }
+    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) {
+        const double2 ri = r[i], di = dinv[i];
+        advance(i, make_double2(di.x * ri.x, di.y * ri.y));
+    }
+}
+
 // r = b - q (true residual), rr_true = r.r
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_true_residual(int64_t n, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
@@ -664,9 +744,10 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
 //            SpMV / update kernel writes its partial into every peer's mailbox and the next kernel sums the W partials
 //            in rank order.  The first iteration after (re)initialisation still uses NCCL for the halo.
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, const DistPlan *dist, double rtol, int maxit,
-                    int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms)
+                    int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms, int prof_every)
 {
     PcgBuffers &w = w_in;
+    if (prof_every < 1) prof_every = 1;
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
     const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
@@ -765,14 +846,32 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
             }
         }
     }
-    const bool pdl = single && w.use_pdl && !prof && ring_on;   // measured: PDL costs time with the row kernel (181 vs 133 us per iteration)
+    // fused update + direction kernel: needs all its CTAs co-resident (software grid barrier)
+    int g_fused = 0;
+    if (single && w.use_fused) {
+        int bps = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_fused, FUSE_BLOCK, 0) == cudaSuccess && bps > 0) {
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int64_t want = (n2 + FUSE_BLOCK - 1) / FUSE_BLOCK, cap = (int64_t)sms * std::min(bps, FUSE_BPS);
+            g_fused = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, cap), PCG_MAX_PART));
+        }
+        if ((e = cudaMemsetAsync(w.counters + 4, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+    }
+    unsigned int fused_k = 0;    // fused launches since the barrier counter was last zeroed
+    const bool pdl = single && w.use_pdl && ring_on && !(prof && prof_every == 1);   // measured: PDL costs time with the row kernel (181 vs 133 us per iteration)
     const int g_ring = w.n_tile < RING_GRID ? w.n_tile : RING_GRID;
     while (it < maxit) {
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
-        cudaEvent_t *ev = prof ? prof + (size_t)pool * 4 * chunk : nullptr;
-        for (int k = 0; k < todo; k++, it++) {
-            if (ev) cudaEventRecord(ev[4 * k], s);
+        cudaEvent_t *ev_pool = prof ? prof + (size_t)pool * 4 * chunk : nullptr;
+        int n_sampled = 0;
+        for (int kk = 0; kk < todo; kk++, it++) {
+            // profile: events around the kernels of every prof_every-th iteration (the others keep their PDL overlap)
+            cudaEvent_t *ev = (ev_pool && it % prof_every == 0) ? ev_pool : nullptr;
+            const int k = n_sampled;
+            if (ev) { n_sampled++; cudaEventRecord(ev[4 * k], s); }
             if (single) {
                 if (ring_on)
                     e = launch_ex(pdl, k_spmv_ring, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile,
@@ -784,6 +883,17 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                                   (const int32_t *)nullptr, (int64_t)0, HaloPush{}, (const double *)nullptr);
                 if (e != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                if (g_fused) {
+                    if ((uint64_t)(fused_k + 1) * (uint64_t)g_fused > 0x7fffffffull) {   // keep the arrival counter inside 32 bits
+                        if ((e = cudaMemsetAsync(w.counters + 4, 0, sizeof(unsigned int), s)) != cudaSuccess) return done(e);
+                        fused_k = 0;
+                    }
+                    ++fused_k;
+                    if ((e = launch_ex(pdl, k_pcg_fused, g_fused, FUSE_BLOCK, 0, s, n2, it, w.sc, p2, (const double2 *)q2, dinv2, x2, r2, w.part_a,
+                                       w.part_b, w.counters + 4, fused_k * (unsigned int)g_fused, err_dev)) != cudaSuccess) return done(e);
+                    if (ev) { cudaEventRecord(ev[4 * k + 2], s); cudaEventRecord(ev[4 * k + 3], s); }
+                    continue;
+                }
                 if ((e = launch_ex(pdl, k_pcg_update<false>, gv, VEC_BLOCK, 0, s, n2, it, w.sc, (const double2 *)p2, (const double2 *)q2, dinv2, x2, r2,
                                    w.part_a, w.part_b, w.counters + 1, NO_P2P, w.sc + sc_rz(it + 1))) != cudaSuccess) return done(e);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);
@@ -824,17 +934,17 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                 if (ev) cudaEventRecord(ev[4 * k + 3], s);
             }
         }
-        if (launches) *launches += 3 * (int64_t)todo;
+        if (launches) *launches += (g_fused ? 2 : 3) * (int64_t)todo;
         harvest();  // events of the previous chunk, while this one runs
         e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
         int err_host = 0;
-        if (peer) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (peer || g_fused) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return done(e);
         if (err_host) return done(cudaErrorLaunchTimeout);   // a peer did not answer within 10 s
-        if (prof) { pend_pool = pool; pend_n = todo; pool ^= 1; }
+        if (prof) { pend_pool = pool; pend_n = n_sampled; pool ^= 1; }
         if (sc_host[SC_DONE] != 0.0) it = (int)sc_host[SC_IT_DONE];   // the device stopped early inside the chunk
         info->iterations = it;
         const double rr = sc_host[sc_rr(it)];

@@ -245,7 +245,7 @@ class Context:
         return self
 
     def set_profile(self, on=True):
-        self._ck(self._L.mofem_set_profile(self._h, int(bool(on))))
+        self._ck(self._L.mofem_set_profile(self._h, int(on)))
         return self
 
     def pcg_profile(self) -> dict:

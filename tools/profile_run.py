@@ -24,6 +24,8 @@ for k in FlatProblem.ARRAYS:
     a = getattr(fp, k)
     if a is not None and k != "elem_mesh":
         setattr(fp, k, torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+pr = torch.cuda.get_device_properties(0)
+print("device", pr.name, "L2", pr.L2_cache_size, {k: getattr(pr, k) for k in dir(pr) if "persist" in k.lower() or "window" in k.lower()})
 ctx = Context(0)
 ctx.set_problem(fp).symbolic().assemble()
 ctx.set_system(torch.from_numpy(rhs).to(dev), torch.from_numpy(fixed).to(dev), torch.from_numpy(val).to(dev))
@@ -32,12 +34,14 @@ runs = []
 if configs:      # e.g. configs=ring:pdl,ring,pdl,none   (each: the switches that are ON)
     for c in configs.split(","):
         on = set(c.split(":"))
-        runs.append(dict(spmv_ring=int("ring" in on), pdl=int("pdl" in on), l2_persist=int("nol2" not in on), profile=int("prof" in on)))
+        win = [int(t[1:]) for t in on if t[:1] == "w" and t[1:].isdigit()]
+        runs.append(dict(spmv_ring=int("ring" in on), pdl=int("pdl" in on), l2_persist=int("nol2" not in on), profile=int("prof" in on),
+                         l2_window=win[0] if win else 5, fused_vec=int("fused" in on)))
 else:
     runs.append(dict(spmv_ring=int(kv.get("spmv_ring", 1)), pdl=int(kv.get("pdl", 1)), l2_persist=int(kv.get("l2_persist", 1)),
-                     profile=int(kv.get("profile", 0))))
+                     profile=int(kv.get("profile", 0)), l2_window=int(kv.get("l2_window", 5)), fused_vec=int(kv.get("fused_vec", 1))))
 for opt in runs:
-    for k in ("spmv_ring", "pdl", "l2_persist"):
+    for k in ("spmv_ring", "pdl", "l2_persist", "l2_window", "fused_vec"):
         ctx.set_option(k, opt[k])
     ctx.set_profile(bool(opt["profile"]))
     best = None
