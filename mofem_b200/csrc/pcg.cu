@@ -282,7 +282,8 @@ int64_t ring_tile_capacity(int64_t n_node, int64_t n_blk) { return (n_node + n_b
 
 // tile t = node rows a with  t*SPAN <= a + node_ptr[a] < (t+1)*SPAN  (the key grows by 1 + degree per row, so a tile
 // holds <= SPAN rows and < SPAN + maxdeg sub-blocks); one thread per tile, two binary searches
-__global__ void k_ring_tiles(int64_t n_node, const int64_t *__restrict__ node_ptr, int n_tile, RingTile *__restrict__ tiles)
+__global__ void k_ring_tiles(int64_t n_node, const int64_t *__restrict__ node_ptr, int n_tile, RingTile *__restrict__ tiles,
+                             const uint8_t *__restrict__ row_mask)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tile) return;
@@ -296,7 +297,9 @@ __global__ void k_ring_tiles(int64_t n_node, const int64_t *__restrict__ node_pt
     };
     const int64_t a0 = first_row_with_key_ge((int64_t)t * PcgRing::SPAN), a1 = first_row_with_key_ge((int64_t)(t + 1) * PcgRing::SPAN);
     RingTile rt;
-    rt.a0 = (int32_t)a0; rt.a1 = (int32_t)a1; rt.b0 = node_ptr[a0]; rt.b1 = node_ptr[a1]; rt._pad = 0;
+    rt.a0 = (int32_t)a0; rt.a1 = (int32_t)a1; rt.b0 = node_ptr[a0]; rt.b1 = node_ptr[a1]; rt.flags = 0;
+    if (row_mask)
+        for (int64_t a = a0; a < a1; a++) if (row_mask[a]) { rt.flags = 1; break; }
     tiles[t] = rt;
 }
 
@@ -315,6 +318,75 @@ k_spmv_ring(int n_tile, const RingTile *__restrict__ tiles, const int64_t *__res
     const double s = block_sum(dot, sm);
     double total;
     if (grid_sum(s, part_dot, counter, sm, total) && threadIdx.x == 0) *dot_out = total;
+}
+
+// Row-partitioned, peer transport: the same ring for the rows that touch no ghost column, with the halo exchange of k_spmv
+// around it -- CTA 0 first stores this rank's boundary entries of x into the neighbours' ghost segments over NVLink and raises
+// its stamp there; the rows that gather ghosts (a compact list, their tiles carry the mask flag) are multiplied after the ring,
+// behind a wait for the neighbours' stamps; the last CTA publishes the p.q partial into every peer's mailbox.
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(PcgRing::CW * 32) : "memory"); }
+
+__global__ void __launch_bounds__(PcgRing::THREADS, 2)
+k_spmv_ring_p2p(int n_tile, const RingTile *__restrict__ tiles, int64_t n_node, const int64_t *__restrict__ node_ptr,
+                const int32_t *__restrict__ node_idx, const double *__restrict__ data, const double *__restrict__ x,
+                double *__restrict__ y, const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter,
+                P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo,
+                const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp, const double *done_flag)
+{
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ double sm[32];
+    if (done_flag && *done_flag != 0.0) return;
+    const bool consumer = (int)(threadIdx.x >> 5) < PcgRing::CW;
+    constexpr int NC = PcgRing::CW * 32;
+    if (blockIdx.x == 0 && hp.n_nb && consumer) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        for (int64_t i = threadIdx.x; i < hp.n_send; i += NC) {
+            const int k = hp.send_nb[i];
+            double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
+            *dst = x2[hp.send_idx[i]];
+        }
+        __threadfence_system();
+        consumer_barrier();
+        if ((int)threadIdx.x < hp.n_nb)
+            *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
+    }
+    double dot = 0.0;
+    ring_spmv_body<PcgRing, false, false, true>(ring_smem, n_tile, tiles, node_ptr, node_idx, data, x, y, fixed, dot, row_halo);
+    constexpr int64_t rows_per_block = NC / SPMV_LANES;
+    const int64_t h0 = (int64_t)blockIdx.x * rows_per_block;
+    if (consumer && h0 < n_halo) {
+        if ((int)threadIdx.x < n_wait)
+            p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+                     pp.stamp, pp.err);
+        consumer_barrier();
+        __threadfence();
+        const int sub = threadIdx.x % SPMV_LANES;
+        for (int64_t i0 = h0; i0 < n_halo; i0 += (int64_t)gridDim.x * rows_per_block) {
+            const int64_t i = i0 + threadIdx.x / SPMV_LANES;
+            const int64_t a = i < n_halo ? halo_rows[i] : -1;
+            double y0 = 0.0, y1 = 0.0;
+            if (a >= 0) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
+#pragma unroll
+            for (int d = SPMV_LANES / 2; d; d >>= 1) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+            }
+            if (a >= 0 && sub == 0) {
+                if (fixed) {
+                    const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
+                    if (fx.x) y0 = 0.0;
+                    if (fx.y) y1 = 0.0;
+                }
+                *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+            }
+        }
+    }
+    (void)n_node;
+    const double s = block_sum(dot, sm);
+    double total;
+    if (grid_sum(s, part_dot, counter, sm, total)) p2p_publish(pp, 0, total, 0.0);
 }
 
 // kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start while its
@@ -580,6 +652,74 @@ k_pcg_fused(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p
     }
 }
 
+// Row-partitioned, peer transport: the same fusion; the wait for the peers' (rz, rr) partials IS the barrier -- the last CTA
+// of this rank publishes the local partials into every peer's mailbox, then every CTA polls its own mailbox slots (all CTAs
+// are co-resident) and sums the W partials in rank order.  The iteration that meets the tolerance still updates x; p is left.
+__global__ void __launch_bounds__(FUSE_BLOCK, FUSE_BPS)
+k_pcg_fused_p2p(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, const double2 *__restrict__ q,
+                const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r, double *__restrict__ part_rz,
+                double *__restrict__ part_rr, unsigned int *counter, P2PDev pp, double tol2, unsigned int *done_counter)
+{
+    __shared__ double sm[FUSE_BLOCK / 32];
+    if (sc[SC_DONE] != 0.0) return;
+    double pq, unused;
+    p2p_collect(pp, 0, pq, unused);
+    const double rz_old = sc[sc_rz(it)];
+    const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    double2 zc[FUSE_EPT];
+    double rz = 0.0, rr = 0.0;
+    auto residual = [&](int64_t i) {
+        const double2 qi = q[i], di = dinv[i];
+        double2 ri = r[i];
+        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
+        r[i] = ri;
+        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
+        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
+        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
+        return z;
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {
+        const int64_t i = tid + e * nth;
+        if (i < n2) zc[e] = residual(i);
+    }
+    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) residual(i);
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    double a, c;
+    if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c)) p2p_publish(pp, 1, a, c);
+    double rz_new, rr_new;
+    p2p_collect(pp, 1, rz_new, rr_new);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr_new; }   // for the host poll
+    const bool converged = rr_new <= tol2;
+    const double beta = (!converged && rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    auto advance = [&](int64_t i, double2 z) {
+        const double2 pi = p[i];
+        double2 xi = x[i];
+        xi.x = fma(alpha, pi.x, xi.x); xi.y = fma(alpha, pi.y, xi.y);
+        x[i] = xi;
+        if (!converged) p[i] = make_double2(fma(beta, pi.x, z.x), fma(beta, pi.y, z.y));
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {
+        const int64_t i = tid + e * nth;
+        if (i < n2) advance(i, zc[e]);
+    }
+    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) {
+        const double2 ri = r[i], di = dinv[i];
+        advance(i, make_double2(di.x * ri.x, di.y * ri.y));
+    }
+    if (converged) {
+        // the LAST CTA to get here raises the stop flag (the others have long passed their entry test): the remaining kernels
+        // of the chunk become no-ops
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+            sc[SC_IT_DONE] = (double)(it + 1); sc[SC_DONE] = 1.0; *done_counter = 0u;
+        }
+    }
+}
+
 // r = b - q (true residual), rr_true = r.r
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_true_residual(int64_t n, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
@@ -710,7 +850,7 @@ cudaError_t pcg_setup(const DevSystem &A, const double *f, const uint8_t *fixed,
         const int64_t nt = (n_own / 2 + A.n_blk + PcgRing::SPAN - 1) / PcgRing::SPAN;
         if (nt <= w.ring_cap && nt < (int64_t)1 << 30) {
             w.n_tile = (int)nt;
-            k_ring_tiles<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(n_own / 2, A.node_ptr, w.n_tile, reinterpret_cast<RingTile *>(w.ring_tiles));
+            k_ring_tiles<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(n_own / 2, A.node_ptr, w.n_tile, reinterpret_cast<RingTile *>(w.ring_tiles), nullptr);
             if (launches) ++*launches;
         }
     }
@@ -773,6 +913,19 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
             if ((e = cudaMalloc(&dmut->halo_rows, sizeof(int32_t) * dmut->halo_rows_cap)) != cudaSuccess) return e;
         }
         dmut->n_halo_rows = (int64_t)rows.size();
+        // tile table of the ring SpMV over the owned rows, tiles with halo rows flagged
+        w.n_tile = 0;
+        if (w.use_ring && w.ring_tiles && n_node) {
+            int64_t blk_own = 0;
+            if ((e = cudaMemcpyAsync(&blk_own, A.node_ptr + n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+            const int64_t nt = (n_node + blk_own + PcgRing::SPAN - 1) / PcgRing::SPAN;
+            if (nt <= w.ring_cap && nt < (int64_t)1 << 30) {
+                w.n_tile = (int)nt;
+                k_ring_tiles<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(n_node, A.node_ptr, w.n_tile, reinterpret_cast<RingTile *>(w.ring_tiles), w.row_halo);
+                if (launches) ++*launches;
+            }
+        }
         if (!rows.empty() &&
             (e = cudaMemcpyAsync(dmut->halo_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -833,7 +986,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
     // single GPU: TMA-ring SpMV (if every node row fits a ring stage) and programmatic dependent launch between the kernels
     const bool single = !(dist && dist->world > 1);
     bool ring_on = false;
-    if (single && w.use_ring && w.n_tile > 0) {
+    if ((single || peer) && w.use_ring && w.n_tile > 0) {
         unsigned int max_deg = 0;
         if ((e = cudaMemcpyAsync(&max_deg, w.counters + 7, sizeof(unsigned int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -842,15 +995,18 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
             static bool attr_set = false;
             if (!attr_set) {
                 if ((e = cudaFuncSetAttribute(k_spmv_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(k_spmv_ring_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
                 attr_set = true;
             }
         }
     }
     // fused update + direction kernel: needs all its CTAs co-resident (software grid barrier)
     int g_fused = 0;
-    if (single && w.use_fused) {
+    if ((single || peer) && w.use_fused) {
         int bps = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_fused, FUSE_BLOCK, 0) == cudaSuccess && bps > 0) {
+        const cudaError_t oe = single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_fused, FUSE_BLOCK, 0)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_fused_p2p, FUSE_BLOCK, 0);
+        if (oe == cudaSuccess && bps > 0) {
             int dev = 0, sms = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -922,11 +1078,23 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
                     hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
                     hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb;
                 }
-                k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
-                                                            w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank,
-                                                            w.row_halo, dist->halo_rows, dist->n_halo_rows, hp, w.sc + SC_DONE);
+                if (ring_on)
+                    k_spmv_ring_p2p<<<g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s>>>(
+                        w.n_tile, reinterpret_cast<const RingTile *>(w.ring_tiles), n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed,
+                        w.part_c, w.counters, pp, fresh ? 0 : dist->n_wait, dist->wait_rank, w.row_halo, dist->halo_rows,
+                        dist->n_halo_rows, hp, w.sc + SC_DONE);
+                else
+                    k_spmv<true, true><<<gs, SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, w.p, w.q, fixed, w.part_c,
+                                                                w.counters, nullptr, pp, fresh ? 0 : dist->n_wait, dist->wait_rank,
+                                                                w.row_halo, dist->halo_rows, dist->n_halo_rows, hp, w.sc + SC_DONE);
                 fresh = false;
                 if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                if (g_fused) {
+                    k_pcg_fused_p2p<<<g_fused, FUSE_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b, w.counters + 1,
+                                                                   pp, tol2, w.counters + 5);
+                    if (ev) { cudaEventRecord(ev[4 * k + 2], s); cudaEventRecord(ev[4 * k + 3], s); }
+                    continue;
+                }
                 k_pcg_update<true><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
                                                            w.counters + 1, pp, nullptr);
                 if (ev) cudaEventRecord(ev[4 * k + 2], s);

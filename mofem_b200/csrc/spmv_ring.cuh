@@ -20,7 +20,7 @@ namespace mofem {
 struct alignas(16) RingTile {
     int64_t b0, b1;   // sub-blocks [b0, b1) of the node-level CSR
     int32_t a0, a1;   // node rows [a0, a1)
-    int64_t _pad;
+    int64_t flags;    // bit 0: some row of the tile is masked (row_skip), consumers then test every row
 };
 
 template <int SPAN_, int MAXDEG_, int STAGES_, int CW_, bool EVICT_FIRST_ = true>
@@ -82,13 +82,15 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 }  // namespace ring
 
 // y = K x on node rows (fixed rows -> 0); returns this thread's share of x.y in `dot` (consumer lanes with sub == 0).
+// MASKED: rows with row_skip[row] != 0 are left out (their tiles carry flag bit 0).
 // Called by every thread of a CTA of Cfg::THREADS threads with Cfg::SMEM_BYTES of dynamic shared memory.
 // node_idx must be readable up to 12 bytes and node_ptr up to 8 bytes past their ends (the copies are 16-byte granular).
-template <class Cfg, bool PDL, bool TRIG_LATE = false>
+template <class Cfg, bool PDL, bool TRIG_LATE = false, bool MASKED = false>
 __device__ __forceinline__ void ring_spmv_body(unsigned char *smem, int n_tile, const RingTile *__restrict__ tiles,
                                                const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
                                                const double *__restrict__ data, const double *__restrict__ x,
-                                               double *__restrict__ y, const uint8_t *__restrict__ fixed, double &dot)
+                                               double *__restrict__ y, const uint8_t *__restrict__ fixed, double &dot,
+                                               const uint8_t *__restrict__ row_skip = nullptr)
 {
     constexpr int S = Cfg::STAGES, CW = Cfg::CW;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * Cfg::STAGE_BYTES);
@@ -112,6 +114,7 @@ __device__ __forceinline__ void ring_spmv_body(unsigned char *smem, int n_tile, 
                 const int2 h1 = __ldg(reinterpret_cast<const int2 *>(tiles + t) + 2);
                 *reinterpret_cast<longlong2 *>(st + Cfg::HDR_OFF) = h0;
                 *reinterpret_cast<int2 *>(st + Cfg::HDR_OFF + 16) = h1;
+                if (MASKED) *reinterpret_cast<long long *>(st + Cfg::HDR_OFF + 24) = __ldg(reinterpret_cast<const long long *>(tiles + t) + 3);
                 const int64_t b0 = h0.x, b1 = h0.y;
                 const int a0 = h1.x, a1 = h1.y;
                 const int64_t i0 = b0 & ~(int64_t)3;
@@ -148,12 +151,14 @@ __device__ __forceinline__ void ring_spmv_body(unsigned char *smem, int n_tile, 
         const int2 h1 = *reinterpret_cast<const int2 *>(st + Cfg::HDR_OFF + 16);
         const int64_t b0 = h0.x;
         const int a0 = h1.x, a1 = h1.y;
+        const bool masked_tile = MASKED && (*reinterpret_cast<const long long *>(st + Cfg::HDR_OFF + 24) & 1);
         const double2 *vs = reinterpret_cast<const double2 *>(st + Cfg::VAL_OFF);
         const int32_t *is = reinterpret_cast<const int32_t *>(st + Cfg::IDX_OFF) + (int)(b0 & 3);
         const int64_t *ps = reinterpret_cast<const int64_t *>(st + Cfg::PTR_OFF) + (a0 & 1);
         for (int rbase = a0 + warp * 4; rbase < a1; rbase += CW * 4) {
             const int row = rbase + grp4;
-            const bool valid = row < a1;
+            bool valid = row < a1;
+            if (MASKED && masked_tile && valid && row_skip[row]) valid = false;   // left to the caller (rows that gather ghosts)
             int off = 0, deg = 0;
             if (valid) {
                 const int64_t r0 = ps[row - a0];
