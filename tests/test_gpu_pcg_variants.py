@@ -1,0 +1,118 @@
+"""The PCG loop's kernel variants (TMA-ring SpMV, fused update+direction kernel with its grid barrier, programmatic dependent
+launch) against the plain three-kernel loop: same iteration, so the displacements agree to round-off of the dot-product order;
+plus the fall-back when a node row is too long for a ring stage, and run-to-run bit reproducibility of the default path."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import load_golden
+from mofem_b200 import overlay_gen
+from mofem_b200.flatten import FlatProblem, material_matrix
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [dict(spmv_ring=1, fused_vec=1, pdl=1), dict(spmv_ring=1, fused_vec=1, pdl=0), dict(spmv_ring=1, fused_vec=0, pdl=1),
+            dict(spmv_ring=0, fused_vec=1, pdl=0), dict(spmv_ring=0, fused_vec=0, pdl=0)]
+
+
+def _restore(ctx):
+    for k in ("spmv_ring", "fused_vec", "pdl"):
+        ctx.set_option(k, 1)
+
+
+def _solve_all(ctx, rtol, maxit=200000):
+    out = []
+    for v in VARIANTS:
+        for k, val in v.items():
+            ctx.set_option(k, val)
+        u, info = ctx.solve(rtol=rtol, maxit=maxit)
+        out.append((u.copy(), info, ctx.energy()))
+    _restore(ctx)
+    return out
+
+
+def test_variants_agree_on_the_patch_family(gpu_ctx):
+    fp, rhs, fixed, val = overlay_gen.patch_family(96)
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    gpu_ctx.set_system(rhs, fixed, val)
+    res = _solve_all(gpu_ctx, 1e-11)
+    u0, i0, e0 = res[-1]                       # the plain loop
+    assert i0["converged"] == 1
+    for u, info, e in res[:-1]:
+        assert info["converged"] == 1 and info["relres_true"] <= 1e-11
+        assert abs(info["iterations"] - i0["iterations"]) <= 3
+        assert np.abs(u - u0).max() <= 1e-9 * np.abs(u0).max()
+        assert abs(e - e0) <= 1e-9 * abs(e0)
+    # against a direct solve of the same matrix
+    indptr, indices, data = gpu_ctx.csr()
+    n = fp.n_dof
+    K = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    free = np.flatnonzero(fixed == 0)
+    ur = val.copy()
+    ur[free] = spla.spsolve(K[free][:, free].tocsc(), (rhs - K @ val)[free])
+    assert np.abs(res[0][0] - ur).max() <= 1e-9 * np.abs(ur).max()
+
+
+@pytest.mark.parametrize("name", ["simpleOFE3", "single_quad", "AMOREBracket"])
+def test_variants_agree_on_reference_problems(gpu_ctx, name):
+    from test_gpu_solve import _full_rhs
+    from conftest import fixed_from_constraints
+    import pickle
+    fp, d = load_golden(name)
+    cons = d["constraints"] if "constraints" in d else pickle.loads(d["deck"].tobytes())[-3]
+    fixed, val = fixed_from_constraints(cons, fp.n_dof)
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    gpu_ctx.set_system(_full_rhs(d, fixed, val, fp.n_dof), fixed, val)
+    res = _solve_all(gpu_ctx, 1e-12, maxit=100000)
+    ur = d["displacement"]
+    for u, info, e in res:
+        assert info["converged"] in (1, 2)
+        assert np.abs(u - ur).max() <= 1e-9 * np.abs(ur).max()
+        assert abs(e - d["energy"][0]) <= 1e-9 * abs(d["energy"][0])
+
+
+def _fan(n_tri):
+    """A hub node shared by n_tri 3-node triangles (single mesh): the hub row has n_tri + 2 sub-blocks."""
+    ang = np.linspace(0.0, 1.5 * np.pi, n_tri + 1)
+    rim = np.stack([np.cos(ang), np.sin(ang)], 1) * (1.0 + 0.1 * np.cos(7 * ang))[:, None]
+    node_xy = np.vstack([[0.0, 0.0], rim])
+    elem = np.full((n_tri, 9), -1, np.int32)
+    elem[:, 0] = 0; elem[:, 1] = np.arange(1, n_tri + 1); elem[:, 2] = np.arange(2, n_tri + 2)
+    D = material_matrix([1000.0, 0.3], 1)
+    return FlatProblem(solver=1, n_mesh=1, node_xy=node_xy, elem_nodes=elem, elem_nn=np.full(n_tri, 3, np.int32),
+                       elem_mat=np.zeros(n_tri, np.int32), elem_mesh=np.zeros(n_tri, np.int32), mat_D=np.array([D]),
+                       cell_elem=np.arange(n_tri, dtype=np.int32).reshape(-1, 1), cell_kind=np.zeros(n_tri, np.int32),
+                       cell_tri_ptr=np.zeros(n_tri + 1, np.int64), tri_xy=np.zeros((0, 3, 2)), tri_rho=np.zeros((0, 3, 1)))
+
+
+@pytest.mark.parametrize("n_tri", [100, 200])      # hub row of 102 sub-blocks (fits a ring stage) and 202 (falls back to the row kernel)
+def test_long_node_rows(gpu_ctx, n_tri):
+    fp = _fan(n_tri)
+    n = fp.n_dof
+    fixed = np.zeros(n, np.uint8); val = np.zeros(n)
+    fixed[2:6] = 1                               # clamp the first two rim nodes
+    val[4] = 0.01
+    rhs = np.zeros(n); rhs[2 * (n_tri // 2) + 1] = -1.0; rhs[0] = 0.5
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    gpu_ctx.set_system(rhs, fixed, val)
+    u, info = gpu_ctx.solve(rtol=1e-12, maxit=100000)
+    assert info["converged"] in (1, 2)
+    indptr, indices, data = gpu_ctx.csr()
+    K = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    assert np.diff(indptr).max() == 2 * (n_tri + 2)
+    free = np.flatnonzero(fixed == 0)
+    ur = val.copy()
+    ur[free] = spla.spsolve(K[free][:, free].tocsc(), (rhs - K @ val)[free])
+    assert np.abs(u - ur).max() <= 1e-9 * np.abs(ur).max()
+
+
+def test_default_path_is_bit_reproducible(gpu_ctx):
+    fp, rhs, fixed, val = overlay_gen.patch_family(64)
+    outs = []
+    for _ in range(3):
+        gpu_ctx.set_problem(fp).symbolic().assemble()
+        gpu_ctx.set_system(rhs, fixed, val)
+        u, info = gpu_ctx.solve(rtol=1e-10)
+        outs.append((u.copy(), info["iterations"]))
+    assert all(np.array_equal(outs[0][0], o[0]) and o[1] == outs[0][1] for o in outs[1:])
