@@ -156,10 +156,12 @@ k_numeric(int64_t n_upair, const int64_t *__restrict__ node_ptr, const int32_t *
     double kxx = 0.0, kxy = 0.0, kyx = 0.0, kyy = 0.0;
     for (int64_t c = cb; c < ce; c++) {
         const uint32_t src = contrib_src[c];
-        const double2 *v = reinterpret_cast<const double2 *>(blk_val + 4 * (int64_t)(src >> 1));
-        const double2 v0 = __ldg(v), v1 = __ldg(v + 1);
-        if (src & 1u) { kxx += v0.x; kxy += v1.x; kyx += v0.y; kyy += v1.y; }
-        else { kxx += v0.x; kxy += v0.y; kyx += v1.x; kyy += v1.y; }
+        // one 256-bit load per contribution (LDG.E.256 on sm_100): the 32-byte sector is looked up once, not twice
+        double a0, a1, a2, a3;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
+                     : "l"(blk_val + 4 * (int64_t)(src >> 1)));
+        if (src & 1u) { kxx += a0; kxy += a2; kyx += a1; kyy += a3; }
+        else { kxx += a0; kxy += a1; kyx += a2; kyy += a3; }
     }
     const int64_t a = pair_row[u];
     const int64_t r0 = node_ptr[a], deg = node_ptr[a + 1] - r0;
