@@ -394,9 +394,9 @@ def main():
             traffic = json.load(f)["dram_bytes_per_launch"]
     if spmv_ms:
         ach = ab["spmv"] / (spmv_ms * 1e-3) / 1e9
-        ring = world == 1
-        roofline = {"kernel": ("k_spmv_ring (block-CSR SpMV of the Jacobi-PCG loop, matrix streamed through shared memory by TMA)" if ring
-                               else "k_spmv (block-CSR SpMV inside Jacobi-PCG, row kernel with in-kernel halo exchange)"),
+        roofline = {"kernel": ("k_spmv_ring (block-CSR SpMV of the Jacobi-PCG loop, matrix streamed through shared memory by TMA)" if world == 1
+                               else "k_spmv_ring_p2p (same ring, halo exchange over NVLink peer memory inside the kernel)" if transport == "peer"
+                               else "k_spmv (block-CSR SpMV inside Jacobi-PCG, row kernel) + NCCL halo exchange"),
                     "bound": "hbm", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                     "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
@@ -406,7 +406,7 @@ def main():
                     "launches_timed": prof["iterations"], "sampled_every": (0 if args.no_profile else max(1, args.profile_every))}
     kernels = {}
     if prof["iterations"]:
-        if world == 1:      # update + direction run as one kernel (grid barrier in between)
+        if prof["direction_ms"] < 0.3 * prof["update_ms"]:      # update + direction ran as one kernel (barrier in between)
             ms = (prof["update_ms"] + prof["direction_ms"]) / iters
             kernels["k_pcg_fused"] = {"avg_launch_ms": ms, "gbs": ab["fused"] / (ms * 1e-3) / 1e9,
                                       "frac_hbm": ab["fused"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
