@@ -203,7 +203,7 @@ def main():
     ap.add_argument("--profile-every", type=int, default=16,
                     help="record CUDA events around the PCG kernels of every N-th iteration of the timed steps (1 = all; the "
                          "sampled iterations lose their launch overlap, so N = 1 costs ~10 %% of the step)")
-    ap.add_argument("--l2-persist", type=int, default=1, help="pin the PCG vectors in L2 (library default: 1)")
+    ap.add_argument("--l2-persist", type=int, default=0, help="L2 persistence window over the PCG vectors (library default: 0)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
     ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
@@ -432,7 +432,7 @@ def main():
         "metric": METRIC, "value": cells_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"syn-1M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
+        "config": {"workload": f"syn-{max(1, round(cells_total / world / 1e6))}M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
                    "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
                    "nnz": info["nnz"], "rtol_true_residual": args.rtol,
                    "l2": "inputs larger than L2 (CSR 0.45 GB, block values 1.6 GB vs 126 MB L2)",

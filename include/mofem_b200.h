@@ -185,9 +185,12 @@ int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double 
  * context's stream, on = N > 1 around those of every N-th iteration (the others keep their launch overlap), 0 = off.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */
 int mofem_set_profile(mofem_ctx *ctx, int on);
-/* Tuning switches: "l2_persist" (default 1) pins the PCG vectors in L2 during mofem_solve; "cell_kernel" (default 0)
- * sends quad4 overlay cells to the warp-cooperative cell kernel instead of the thread-per-block kernels (bit-identical
- * results, measured slower on B200 -- see DESIGN.md; set before mofem_symbolic). */
+/* Tuning switches (defaults in brackets): "spmv_ring" [1] PCG SpMV streams the matrix through shared memory with the TMA
+ * (0: row kernel); "fused_vec" [1] update + direction of a PCG iteration as one kernel; "pdl" [1] programmatic dependent launch
+ * between the PCG kernels (single GPU, with the ring); "l2_persist" [0] / "l2_window" [5] L2 persistence window over the first
+ * N PCG vectors during mofem_solve (measured neutral at 1 M cells, harmful at 10 M); "cell_kernel" [0] sends quad4 overlay
+ * cells to the warp-cooperative cell kernel instead of the thread-per-block kernels (bit-identical results, measured slower on
+ * B200 -- see DESIGN.md; set before mofem_symbolic). */
 int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value);
 int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations);
 

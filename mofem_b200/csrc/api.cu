@@ -37,7 +37,7 @@ struct mofem_ctx {
     size_t slab_hot_bytes = 0, slab_vec_bytes = 0;
     int l2_window = 5;    // leading vectors of the slab (p, r, dinv, q, x) inside the L2 persistence window
     bool slab_in_xbuf = false;
-    int l2_persist = 1;   // keep the PCG vectors L2-resident while the matrix streams past them
+    int l2_persist = 0;   // L2 persistence window over the PCG vectors: neutral at 1 M cells since the matrix stream carries evict-first hints, costs 20 % at 10 M (measured) -> off
     int spmv_ring = 1;    // PCG SpMV streams the matrix through shared memory with the TMA (spmv_ring.cuh); 0: row kernel
     int fused_vec = 1;    // update + direction of a PCG iteration as one kernel with a grid barrier (single GPU)
     int pdl = 1;          // programmatic dependent launch between the three kernels of a PCG iteration (single GPU)

@@ -574,14 +574,95 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
     }
 }
 
-// ---- single GPU: update and direction in ONE kernel -------------------------------------------------------------------
+// ---- update and direction in ONE kernel ---------------------------------------------------------------------------------
 //   phase 1   r -= alpha q ; z = dinv r ; partials of r.z and r.r                 (alpha = rz / p.q)
-//   grid barrier (all CTAs are co-resident: the grid is sized by the occupancy query); every CTA then sums the partials in
-//   index order -- the same bits everywhere, no "last block" tail
+//   barrier   single GPU: a grid barrier (all CTAs are co-resident: the grid is sized by the occupancy query), after which
+//             every CTA sums the partials in index order -- the same bits everywhere, no "last block" tail;
+//             peer transport: the wait for the peers' partials (below)
 //   phase 2   x += alpha p ; p = z + beta p                                       (beta = rz_new / rz)
-// z of the first FUSE_EPT elements of a thread stays in registers across the barrier, so every vector is read once per
-// iteration (q r dinv | p x in, r | x p out: 88 MB instead of 121 MB at the 1 M-cell bench size) and one launch goes away.
-constexpr int FUSE_BLOCK = 256, FUSE_EPT = 5, FUSE_BPS = 4;
+// A thread owns the elements tid, tid + T, tid + 2T, ... and walks them in batches of FUSE_EPT with the loads of a batch
+// issued together; z of the FIRST batch stays in registers across the barrier (all of z at the 1 M-cell bench size: 3 CTAs
+// of 256 threads per SM own 6.07 elements per thread), the
+// later batches re-read r and dinv.  Every vector is then read once per iteration (q r dinv | p x in, r | x p out: 88 MB
+// instead of 121 MB at the bench size) and one launch goes away.
+constexpr int FUSE_BLOCK = 256, FUSE_EPT = 6, FUSE_BPS = 3;
+
+__device__ __forceinline__ void fused_phase1(int64_t n2, int64_t tid, int64_t nth, double alpha, const double2 *__restrict__ q,
+                                             const double2 *__restrict__ dinv, double2 *__restrict__ r, double2 (&zc)[FUSE_EPT],
+                                             double &rz, double &rr)
+{
+    auto residual = [&](int64_t i, double2 qi, double2 di, double2 ri) {
+        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
+        r[i] = ri;
+        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
+        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
+        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
+        return z;
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {       // first batch: z stays in registers (the compiler interleaves the loads)
+        const int64_t i = tid + e * nth;
+        if (i < n2) zc[e] = residual(i, q[i], dinv[i], r[i]);
+    }
+    constexpr int B1 = 2;                      // later batches (large problems, DRAM-bound): loads of a batch issued together
+    for (int64_t base = tid + FUSE_EPT * nth; base < n2; base += B1 * nth) {
+        double2 qv[B1], dv[B1], rv[B1];
+#pragma unroll
+        for (int e = 0; e < B1; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) { qv[e] = q[i]; dv[e] = dinv[i]; rv[e] = r[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < B1; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) residual(i, qv[e], dv[e], rv[e]);
+        }
+    }
+}
+
+template <bool UPDATE_P>
+__device__ __forceinline__ void fused_phase2(int64_t n2, int64_t tid, int64_t nth, double alpha, double beta,
+                                             const double2 *__restrict__ dinv, const double2 *__restrict__ r,
+                                             double2 *__restrict__ x, double2 *__restrict__ p, const double2 (&zc)[FUSE_EPT])
+{
+    {   // first batch: z from registers
+        double2 pv[FUSE_EPT], xv[FUSE_EPT];
+#pragma unroll
+        for (int e = 0; e < FUSE_EPT; e++) {
+            const int64_t i = tid + e * nth;
+            if (i < n2) { pv[e] = p[i]; xv[e] = x[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < FUSE_EPT; e++) {
+            const int64_t i = tid + e * nth;
+            if (i < n2) {
+                x[i] = make_double2(fma(alpha, pv[e].x, xv[e].x), fma(alpha, pv[e].y, xv[e].y));
+                if (UPDATE_P) p[i] = make_double2(fma(beta, pv[e].x, zc[e].x), fma(beta, pv[e].y, zc[e].y));
+            }
+        }
+    }
+    constexpr int B2 = 2;   // later batches (large problems, DRAM-bound): z recomputed from r and dinv
+    for (int64_t base = tid + FUSE_EPT * nth; base < n2; base += B2 * nth) {
+        double2 pv[B2], xv[B2], rv[B2], dv[B2];
+#pragma unroll
+        for (int e = 0; e < B2; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) {
+                pv[e] = p[i]; xv[e] = x[i];
+                if (UPDATE_P) { rv[e] = r[i]; dv[e] = dinv[i]; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < B2; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) {
+                x[i] = make_double2(fma(alpha, pv[e].x, xv[e].x), fma(alpha, pv[e].y, xv[e].y));
+                if (UPDATE_P) p[i] = make_double2(fma(beta, pv[e].x, dv[e].x * rv[e].x), fma(beta, pv[e].y, dv[e].y * rv[e].y));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_BPS)
 k_pcg_fused(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, const double2 *__restrict__ q,
             const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r, double *__restrict__ part_rz,
@@ -594,22 +675,7 @@ k_pcg_fused(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     double2 zc[FUSE_EPT];
     double rz = 0.0, rr = 0.0;
-    auto residual = [&](int64_t i) {
-        const double2 qi = q[i], di = dinv[i];
-        double2 ri = r[i];
-        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
-        r[i] = ri;
-        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
-        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
-        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
-        return z;
-    };
-#pragma unroll
-    for (int e = 0; e < FUSE_EPT; e++) {
-        const int64_t i = tid + e * nth;
-        if (i < n2) zc[e] = residual(i);
-    }
-    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) residual(i);
+    fused_phase1(n2, tid, nth, alpha, q, dinv, r, zc, rz, rr);
     const double s1 = block_sum(rz, sm);
     const double s2 = block_sum(rr, sm);
     // grid barrier: monotonically increasing arrival counter (zeroed by the host), one arrival per CTA
@@ -634,22 +700,7 @@ k_pcg_fused(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr_new; }
     ring::grid_dep_launch();      // the next SpMV may become resident from here on (its producer warp pre-fills the ring)
     const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
-    auto advance = [&](int64_t i, double2 z) {
-        const double2 pi = p[i];
-        double2 xi = x[i];
-        xi.x = fma(alpha, pi.x, xi.x); xi.y = fma(alpha, pi.y, xi.y);
-        x[i] = xi;
-        p[i] = make_double2(fma(beta, pi.x, z.x), fma(beta, pi.y, z.y));
-    };
-#pragma unroll
-    for (int e = 0; e < FUSE_EPT; e++) {
-        const int64_t i = tid + e * nth;
-        if (i < n2) advance(i, zc[e]);
-    }
-    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) {
-        const double2 ri = r[i], di = dinv[i];
-        advance(i, make_double2(di.x * ri.x, di.y * ri.y));
-    }
+    fused_phase2<true>(n2, tid, nth, alpha, beta, dinv, r, x, p, zc);
 }
 
 // Row-partitioned, peer transport: the same fusion; the wait for the peers' (rz, rr) partials IS the barrier -- the last CTA
@@ -669,22 +720,7 @@ k_pcg_fused_p2p(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     double2 zc[FUSE_EPT];
     double rz = 0.0, rr = 0.0;
-    auto residual = [&](int64_t i) {
-        const double2 qi = q[i], di = dinv[i];
-        double2 ri = r[i];
-        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
-        r[i] = ri;
-        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
-        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
-        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
-        return z;
-    };
-#pragma unroll
-    for (int e = 0; e < FUSE_EPT; e++) {
-        const int64_t i = tid + e * nth;
-        if (i < n2) zc[e] = residual(i);
-    }
-    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) residual(i);
+    fused_phase1(n2, tid, nth, alpha, q, dinv, r, zc, rz, rr);
     const double s1 = block_sum(rz, sm);
     const double s2 = block_sum(rr, sm);
     double a, c;
@@ -694,23 +730,9 @@ k_pcg_fused_p2p(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr_new; }   // for the host poll
     const bool converged = rr_new <= tol2;
     const double beta = (!converged && rz_old != 0.0) ? rz_new / rz_old : 0.0;
-    auto advance = [&](int64_t i, double2 z) {
-        const double2 pi = p[i];
-        double2 xi = x[i];
-        xi.x = fma(alpha, pi.x, xi.x); xi.y = fma(alpha, pi.y, xi.y);
-        x[i] = xi;
-        if (!converged) p[i] = make_double2(fma(beta, pi.x, z.x), fma(beta, pi.y, z.y));
-    };
-#pragma unroll
-    for (int e = 0; e < FUSE_EPT; e++) {
-        const int64_t i = tid + e * nth;
-        if (i < n2) advance(i, zc[e]);
-    }
-    for (int64_t i = tid + FUSE_EPT * nth; i < n2; i += nth) {
-        const double2 ri = r[i], di = dinv[i];
-        advance(i, make_double2(di.x * ri.x, di.y * ri.y));
-    }
-    if (converged) {
+    if (!converged) fused_phase2<true>(n2, tid, nth, alpha, beta, dinv, r, x, p, zc);
+    else {
+        fused_phase2<false>(n2, tid, nth, alpha, beta, dinv, r, x, p, zc);
         // the LAST CTA to get here raises the stop flag (the others have long passed their entry test): the remaining kernels
         // of the chunk become no-ops
         __syncthreads();
