@@ -289,13 +289,19 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
     CKT(csr_fill_rows(P, T, C.row_start, row_cnt, entries, s)); L++;
     CKT(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
-    CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, s)); L++;
+    CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, 0, s)); L++;   // rank sort of the short rows
     CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
-    if (eflag == MOFEM_E_LIMIT) {  // some node row has > 1024 contributions: redo with a global scratch area
-        uint64_t *scratch;
-        if ((rc = dev_alloc(ctx, &scratch, 2 * C.n_entry, tmp))) { cleanup(); return rc; }
-        CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, scratch, ctx->err_flag, s)); L++;
+    if (eflag) {                   // some node rows have > 256 contributions: bitonic sort for those
+        CKT(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
+        CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, 1, s)); L++;
+        CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CKT(cudaStreamSynchronize(s));
+        if (eflag == MOFEM_E_LIMIT) {  // ... and some > 1024: redo those with a global scratch area
+            uint64_t *scratch;
+            if ((rc = dev_alloc(ctx, &scratch, 2 * C.n_entry, tmp))) { cleanup(); return rc; }
+            CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, scratch, ctx->err_flag, 1, s)); L++;
+        }
     }
     CKT(exclusive_scan_i32_to_i64(row_uniq, C.node_ptr, P.n_node, C.node_ptr + P.n_node, s, &L));
     CKT(cudaMemcpyAsync(&C.n_upair, C.node_ptr + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));

@@ -90,7 +90,7 @@ cudaError_t csr_count_rows(const DevProblem &p, const DevTasks &t, int32_t *row_
 cudaError_t csr_fill_rows(const DevProblem &p, const DevTasks &t, const int64_t *row_start, int32_t *row_cursor,
                           uint64_t *entries, cudaStream_t s);
 cudaError_t csr_sort_rows(int64_t n_node, const int64_t *row_start, uint64_t *entries, int32_t *row_uniq,
-                          uint64_t *scratch, int *err_flag, cudaStream_t s);
+                          uint64_t *scratch, int *err_flag, int phase, cudaStream_t s);
 cudaError_t csr_emit(int64_t n_node, const int64_t *row_start, const uint64_t *entries, const int64_t *node_ptr,
                      int32_t *node_idx, int32_t *pair_row, int64_t *contrib_ptr, uint32_t *contrib_src, cudaStream_t s);
 cudaError_t csr_numeric(const DevCsr &c, const double *blk_val, double *data, cudaStream_t s);

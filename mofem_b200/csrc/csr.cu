@@ -82,7 +82,7 @@ __device__ __forceinline__ void warp_bitonic(uint64_t *keys, int P, int lane)
 
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_rows(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__restrict__ entries,
-            int32_t *__restrict__ row_uniq, uint64_t *__restrict__ scratch, int *err_flag)
+            int32_t *__restrict__ row_uniq, uint64_t *__restrict__ scratch, int *err_flag, int64_t min_len)
 {
     __shared__ uint64_t sm[SORT_WARPS][SORT_SMEM_KEYS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -90,7 +90,7 @@ k_sort_rows(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__r
     if (row >= n_node) return;
     const int64_t b = row_start[row];
     const int64_t L = row_start[row + 1] - b;
-    if (L == 0) { if (lane == 0) row_uniq[row] = 0; return; }
+    if (L <= min_len) return;        // short rows were sorted by k_sort_rows_rank
     uint64_t *keys;
     int P = 1;
     while (P < L) P <<= 1;
@@ -107,6 +107,67 @@ k_sort_rows(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__r
         const uint64_t kx = keys[i];
         entries[b + i] = kx;
         if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != (uint32_t)(kx >> 32)) uniq++;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, d);
+    if (lane == 0) row_uniq[row] = uniq;
+}
+
+// Short rows (<= RANK_MAX contributions; the bench matrix averages 71 per node row): rank sort -- every lane holds up to M of
+// the row's keys in registers and counts, over one broadcast pass through the row in shared memory, how many keys are smaller;
+// the rank IS the sorted position (keys are distinct: src is unique).  No padding to a power of two, no stage barriers:
+// ~2x faster than the bitonic network at these lengths.  Longer rows are left to k_sort_rows (flagged through *long_rows).
+constexpr int RANK_WARPS = 8;
+constexpr int RANK_MAX = 256;
+
+template <int M>
+__device__ __forceinline__ void warp_rank_sort(const uint64_t *__restrict__ keys, uint64_t *__restrict__ sorted, int L, int lane)
+{
+    uint64_t k[M];
+    int rank[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) { const int i = lane + 32 * m; k[m] = i < L ? keys[i] : ~0ull; rank[m] = 0; }
+    for (int j = 0; j < L; j++) {
+        const uint64_t kj = keys[j];
+#pragma unroll
+        for (int m = 0; m < M; m++) rank[m] += (kj < k[m]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++) if (lane + 32 * m < L) sorted[rank[m]] = k[m];
+}
+
+__global__ void __launch_bounds__(RANK_WARPS * 32)
+k_sort_rows_rank(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__restrict__ entries,
+                 int32_t *__restrict__ row_uniq, int *long_rows)
+{
+    __shared__ uint64_t sm_in[RANK_WARPS][RANK_MAX], sm_out[RANK_WARPS][RANK_MAX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * RANK_WARPS + w;
+    if (row >= n_node) return;
+    const int64_t b = row_start[row];
+    const int64_t L64 = row_start[row + 1] - b;
+    if (L64 == 0) { if (lane == 0) row_uniq[row] = 0; return; }
+    if (L64 > RANK_MAX) { if (lane == 0) *long_rows = 1; return; }
+    const int L = (int)L64;
+    uint64_t *keys = sm_in[w], *sorted = sm_out[w];
+    for (int i = lane; i < L; i += 32) keys[i] = entries[b + i];
+    __syncwarp();
+    switch ((L + 31) >> 5) {
+    case 1: warp_rank_sort<1>(keys, sorted, L, lane); break;
+    case 2: warp_rank_sort<2>(keys, sorted, L, lane); break;
+    case 3: warp_rank_sort<3>(keys, sorted, L, lane); break;
+    case 4: warp_rank_sort<4>(keys, sorted, L, lane); break;
+    case 5: warp_rank_sort<5>(keys, sorted, L, lane); break;
+    case 6: warp_rank_sort<6>(keys, sorted, L, lane); break;
+    case 7: warp_rank_sort<7>(keys, sorted, L, lane); break;
+    default: warp_rank_sort<8>(keys, sorted, L, lane); break;
+    }
+    __syncwarp();
+    int uniq = 0;
+    for (int i = lane; i < L; i += 32) {
+        const uint64_t kx = sorted[i];
+        entries[b + i] = kx;
+        if (i == 0 || (uint32_t)(sorted[i - 1] >> 32) != (uint32_t)(kx >> 32)) uniq++;
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, d);
@@ -209,12 +270,18 @@ cudaError_t csr_fill_rows(const DevProblem &p, const DevTasks &t, const int64_t 
     return cudaGetLastError();
 }
 
+// phase 0: rank sort of the short rows, *err_flag = 1 if longer rows exist; phase 1: bitonic sort of the rows longer than
+// RANK_MAX (shared memory up to 1024 keys, else `scratch`; *err_flag = MOFEM_E_LIMIT if scratch is needed but null)
 cudaError_t csr_sort_rows(int64_t n_node, const int64_t *row_start, uint64_t *entries, int32_t *row_uniq,
-                          uint64_t *scratch, int *err_flag, cudaStream_t s)
+                          uint64_t *scratch, int *err_flag, int phase, cudaStream_t s)
 {
     if (n_node == 0) return cudaSuccess;
-    k_sort_rows<<<(unsigned)((n_node + SORT_WARPS - 1) / SORT_WARPS), SORT_WARPS * 32, 0, s>>>(
-        n_node, row_start, entries, row_uniq, scratch, err_flag);
+    if (phase == 0)
+        k_sort_rows_rank<<<(unsigned)((n_node + RANK_WARPS - 1) / RANK_WARPS), RANK_WARPS * 32, 0, s>>>(n_node, row_start, entries,
+                                                                                                       row_uniq, err_flag);
+    else
+        k_sort_rows<<<(unsigned)((n_node + SORT_WARPS - 1) / SORT_WARPS), SORT_WARPS * 32, 0, s>>>(
+            n_node, row_start, entries, row_uniq, scratch, err_flag, (int64_t)RANK_MAX);
     return cudaGetLastError();
 }
 
