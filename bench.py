@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
     ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: ONE n0 x n0 problem cut into N strips (BASELINE configs 4 and 5) instead of a stack of N blocks "
+                         "of n0 x n0 (weak scaling, the default); n0 / 8 must be a multiple of N")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything else a library prints to fd 1 (e.g. NCCL's version banner) goes
     # to stderr for the rest of the run
@@ -241,24 +244,30 @@ def main():
     else:
         from mofem_b200.distributed import init_comm
         from mofem_b200.partition import exchange_send_lists, partition_problem
-        ny = args.n0 * world
-        per = args.n0 // 8
+        px = args.n0 // 8                                  # patches per patch row
+        if args.strong:
+            if px % world:
+                raise SystemExit("--strong needs n0 / 8 to be a multiple of the number of GPUs")
+            ny, per = args.n0, px // world                 # one n0 x n0 problem, `per` patch rows (8 * per element rows) per rank
+        else:
+            ny, per = args.n0 * world, px                  # a stack of N blocks of n0 x n0
+        rows_per_rank = 8 * per
         strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per), n_mesh=args.meshes)
         n_node0 = (args.n0 + 1) * (ny + 1)
         owner = np.empty(strip.n_node, np.int32)
-        owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // args.n0, world - 1)
-        owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // per) // per
+        owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // rows_per_rank, world - 1)
+        owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // px) // per
         # weak scaling keeps the physics per block fixed: every block carries the corner load of the 1-GPU problem on
         # its own bottom-right node (a single load on a domain N times taller would need ~N times more CG iterations
-        # just to propagate across the height)
-        for r in range(1, world):
+        # just to propagate across the height); strong scaling solves the one problem as it is
+        for r in range(1, world if not args.strong else 1):
             nd = r * args.n0 * (args.n0 + 1) + args.n0
             rhs_g[2 * nd] = 1.0; rhs_g[2 * nd + 1] = -0.5
         part = partition_problem(strip, owner, rank, world)
         fp = part.fp
         rhs, fixed, val = part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g)
         # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
-        own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)
+        own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)      # (one mesh-0 element row per strip boundary)
         del strip, rhs_g, fixed_g, val_g, owner
 
     torch.cuda.set_device(local)
@@ -430,15 +439,17 @@ def main():
     cells_total = fp.n_cell if world == 1 else n_cells_global
     out = {
         "metric": METRIC, "value": cells_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"syn-{max(1, round(cells_total / world / 1e6))}M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
+        "config": {"workload": f"syn-{max(1, round(cells_total / (1 if args.strong else world) / 1e6))}M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
                    "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
                    "nnz": info["nnz"], "rtol_true_residual": args.rtol,
-                   "l2": "inputs larger than L2 (CSR 0.45 GB, block values 1.6 GB vs 126 MB L2)",
+                   "l2": f"inputs larger than L2 (per GPU: CSR {9 * info['nnz'] / 1e9:.2f} GB, block values {32 * info['n_pair'] / 1e9:.2f} GB vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else
                    f"{world} GPUs: cells sharded by strip (no assembly exchange), row-partitioned PCG, halo "
-                   f"exchange + all-reduce over {transport}; global problem {args.n0} x {args.n0 * world} mesh-0 elements, one corner load per block",
+                   f"exchange + all-reduce over {transport}; global problem "
+                   + (f"{args.n0} x {args.n0} mesh-0 elements cut into {world} strips, one corner load" if args.strong else
+                      f"{args.n0} x {args.n0 * world} mesh-0 elements, one corner load per block"),
                    "cells_global": cells_total},
         "e2e": {"value": cells_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_s * 1e3},
