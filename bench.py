@@ -207,6 +207,8 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
     ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
+    ap.add_argument("--host-overlay", action="store_true",
+                    help="1 GPU: build the overlay with the NumPy generator instead of the CUDA one (same bits; untimed either way)")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: ONE n0 x n0 problem cut into N strips (BASELINE configs 4 and 5) instead of a stack of N blocks "
                          "of n0 x n0 (weak scaling, the default); n0 / 8 must be a multiple of N")
@@ -239,7 +241,14 @@ def main():
     t0 = time.perf_counter()
     part = None
     n_cells_global = None
-    if world == 1:
+    overlay_ms = None
+    if world == 1 and not args.host_overlay:
+        # overlay by pairwise convex clipping on the GPU (csrc/overlay.cu; bit-identical to the NumPy generator)
+        from mofem_b200.overlay_gen import patch_family_gpu
+        torch.cuda.set_device(local)
+        with Context(local) as gen_ctx:
+            fp, rhs, fixed, val, overlay_ms = patch_family_gpu(gen_ctx, args.n0, n_mesh=args.meshes, to_host=True)
+    elif world == 1:
         fp, rhs, fixed, val = patch_family(args.n0, n_mesh=args.meshes)
     else:
         from mofem_b200.distributed import init_comm
@@ -279,7 +288,8 @@ def main():
         dist.all_reduce(t)
         n_cells_global = int(t.item())
     prep_s = time.perf_counter() - t0
-    log(f"[rank {rank}] generated n0={args.n0}: {fp.n_cell} cells, {fp.n_tri} triangles, {fp.n_dof} local DOF in {prep_s:.1f}s")
+    log(f"[rank {rank}] generated n0={args.n0}: {fp.n_cell} cells, {fp.n_tri} triangles, {fp.n_dof} local DOF in {prep_s:.1f}s"
+        + (f" (overlay kernels {overlay_ms:.2f} ms)" if overlay_ms is not None else ""))
 
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
@@ -464,6 +474,8 @@ def main():
         "kernels": kernels,
         "energy": last["energy"],
         "prep_s": prep_s,
+        "overlay": ({"where": "gpu (csrc/overlay.cu, pairwise convex clipping)", "kernels_ms": overlay_ms} if overlay_ms is not None
+                    else {"where": "host (mofem_b200/overlay_gen.py)"}),
     }
     emit(out)
     if world > 1:

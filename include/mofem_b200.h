@@ -181,6 +181,19 @@ int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double 
                    int64_t n_elem, const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho,
                    int64_t *newton_updates, double *kernel_ms);
 
+/* Overlay of the structured patch family on the GPU (mesh 0 = nx x ny quadrilaterals, nx and ny multiples of 8;
+ * meshes >= 1 = disjoint 5 x 5 patches, one per 8 x 8 period, straight patch borders): replaces, for this family, the host
+ * pipeline computGeometry/planeSweepMeshes.py:meshOverlay:354 + rhoCalculation:991 + triangulation.py:polygonTriangulation +
+ * the flattening of the object graph.  Inputs: X0 [ny+1][nx+1][2] mesh-0 node coordinates, X1 [ny/8][nx/8][6][6][2] patch node
+ * coordinates; [b_lo, b_hi) = patch rows to emit (plus the mesh-0 element row below them), n_mesh = 2, or 3 (patch (a, b) in mesh
+ * 1 + (a + b) % 2).  Outputs = the cell / triangle arrays of mofem_problem_t, sized by mofem_overlay_patch_sizes
+ * (sizes = {regular cells, ring cells, two-element cells, triangles, cells}); all pointers host or device.  The result is
+ * bit-identical to mofem_b200/overlay_gen.py, which is pinned against the reference's own sweep. */
+int mofem_overlay_patch_sizes(int32_t nx, int32_t ny, int32_t b_lo, int32_t b_hi, int32_t n_mesh, int64_t sizes[5]);
+int mofem_overlay_patch_family(mofem_ctx *ctx, int32_t nx, int32_t ny, int32_t b_lo, int32_t b_hi, int32_t n_mesh, const double *X0,
+                               const double *X1, int32_t *cell_elem, int32_t *cell_kind, int64_t *cell_tri_ptr, double *tri_xy,
+                               double *tri_rho, double *kernel_ms);
+
 /* Per-kernel profile of the PCG loop: on = 1 records CUDA events around the kernels of every iteration of mofem_solve on the
  * context's stream, on = N > 1 around those of every N-th iteration (the others keep their launch overlap), 0 = off.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
  * kernels of the last mofem_solve, *iterations = iterations profiled. */

@@ -42,7 +42,7 @@ EXPORTS = ("mofem_create", "mofem_destroy", "mofem_last_error", "mofem_version",
            "mofem_symbolic", "mofem_assemble", "mofem_get_info", "mofem_get_csr", "mofem_get_coo_values",
            "mofem_set_system", "mofem_solve", "mofem_energy", "mofem_spmv", "mofem_assemble_solve", "mofem_get_timing", "mofem_set_profile",
            "mofem_get_pcg_profile", "mofem_dist_unique_id", "mofem_dist_init", "mofem_set_halo", "mofem_clear_halo", "mofem_set_option", "mofem_p2p_export", "mofem_p2p_import",
-           "mofem_p2p_close", "mofem_sample", "mofem_rho_eval")
+           "mofem_p2p_close", "mofem_sample", "mofem_rho_eval", "mofem_overlay_patch_sizes", "mofem_overlay_patch_family")
 
 _lib = None
 
@@ -85,6 +85,8 @@ def load():
     L.mofem_p2p_close.argtypes = [vp]; L.mofem_p2p_close.restype = C.c_int
     L.mofem_sample.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int64, c_i64_p]; L.mofem_sample.restype = C.c_int
     L.mofem_rho_eval.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, c_i64_p, c_d_p]; L.mofem_rho_eval.restype = C.c_int
+    L.mofem_overlay_patch_sizes.argtypes = [C.c_int32] * 5 + [c_i64_p]; L.mofem_overlay_patch_sizes.restype = C.c_int
+    L.mofem_overlay_patch_family.argtypes = [vp] + [C.c_int32] * 5 + [vp] * 7 + [c_d_p]; L.mofem_overlay_patch_family.restype = C.c_int
     L.mofem_set_profile.argtypes = [vp, C.c_int]; L.mofem_set_profile.restype = C.c_int
     L.mofem_set_option.argtypes = [vp, C.c_char_p, C.c_int64]; L.mofem_set_option.restype = C.c_int
     L.mofem_get_pcg_profile.argtypes = [vp, c_d_p, c_i64_p]; L.mofem_get_pcg_profile.restype = C.c_int

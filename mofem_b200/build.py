@@ -18,6 +18,7 @@ SOURCES = {
     "integrate.cu": ["-fmad=false"],
     "sample.cu": ["-fmad=false"],
     "rho.cu": ["-fmad=false"],
+    "overlay.cu": ["-fmad=false"],
     "csr.cu": [],
     "scan.cu": [],
     "pcg.cu": [],

@@ -882,6 +882,61 @@ int mofem_rho_eval(mofem_ctx *ctx, int64_t n_vert, int32_t n_mesh, const double 
     return MOFEM_OK;
 }
 
+// ---- overlay of the structured patch family ----------------------------------------
+static bool overlay_args_ok(int32_t nx, int32_t ny, int32_t b_lo, int32_t b_hi, int32_t n_mesh)
+{
+    return nx >= 8 && ny >= 8 && nx % 8 == 0 && ny % 8 == 0 && b_lo >= 0 && b_lo < b_hi && b_hi <= ny / 8 && (n_mesh == 2 || n_mesh == 3);
+}
+
+int mofem_overlay_patch_sizes(int32_t nx, int32_t ny, int32_t b_lo, int32_t b_hi, int32_t n_mesh, int64_t sizes[5])
+{
+    if (!sizes || !overlay_args_ok(nx, ny, b_lo, b_hi, n_mesh)) return MOFEM_E_ARG;
+    overlay_sizes(nx, ny, b_lo, b_hi, n_mesh, sizes);
+    return MOFEM_OK;
+}
+
+int mofem_overlay_patch_family(mofem_ctx *ctx, int32_t nx, int32_t ny, int32_t b_lo, int32_t b_hi, int32_t n_mesh, const double *X0,
+                               const double *X1, int32_t *cell_elem, int32_t *cell_kind, int64_t *cell_tri_ptr, double *tri_xy,
+                               double *tri_rho, double *kernel_ms)
+{
+    if (!ctx) return MOFEM_E_ARG;
+    if (!overlay_args_ok(nx, ny, b_lo, b_hi, n_mesh)) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_overlay_patch_family: nx, ny must be multiples of 8, 0 <= b_lo < b_hi <= ny / 8, n_mesh 2 or 3");
+    if (!X0 || !X1 || !cell_elem || !cell_kind || !cell_tri_ptr || !tri_xy || !tri_rho) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_overlay_patch_family: null array");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int64_t sz[5];
+    overlay_sizes(nx, ny, b_lo, b_hi, n_mesh, sz);
+    const int64_t n_cell = sz[4], n_tri = sz[3];
+    if (n_cell >= ((int64_t)1 << 31)) return ctx_fail(ctx, MOFEM_E_LIMIT, "mofem_overlay_patch_family: more than 2^31 cells");
+    std::vector<void *> tmp;
+    int rc;
+    const double *x0d, *x1d;
+    if ((rc = upload(ctx, X0, 2 * (int64_t)(nx + 1) * (ny + 1), &x0d, tmp)) ||
+        (rc = upload(ctx, X1, 72 * (int64_t)(nx / 8) * (ny / 8), &x1d, tmp))) { free_pool(ctx, tmp); return rc; }
+    int32_t *ce = cell_elem, *ck = cell_kind; int64_t *tp = cell_tri_ptr; double *txy = tri_xy, *trho = tri_rho;
+    const bool h_ce = !is_device_ptr(cell_elem), h_ck = !is_device_ptr(cell_kind), h_tp = !is_device_ptr(cell_tri_ptr),
+               h_xy = !is_device_ptr(tri_xy), h_rho = !is_device_ptr(tri_rho);
+    if ((h_ce && (rc = dev_alloc(ctx, &ce, n_cell * n_mesh, tmp))) || (h_ck && (rc = dev_alloc(ctx, &ck, n_cell, tmp))) ||
+        (h_tp && (rc = dev_alloc(ctx, &tp, n_cell + 1, tmp))) || (h_xy && (rc = dev_alloc(ctx, &txy, 6 * n_tri, tmp))) ||
+        (h_rho && (rc = dev_alloc(ctx, &trho, 3 * n_tri * n_mesh, tmp)))) { free_pool(ctx, tmp); return rc; }
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { free_pool(ctx, tmp); return ctx_fail(ctx, MOFEM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+    tic(ctx);
+    CKS(overlay_run(nx, ny, b_lo, b_hi, n_mesh, x0d, x1d, ce, ck, tp, txy, trho, s));
+    CKS(cudaEventRecord(ctx->ev1, s));
+    if (h_ce) CKS(cudaMemcpyAsync(cell_elem, ce, sizeof(int32_t) * n_cell * n_mesh, cudaMemcpyDeviceToHost, s));
+    if (h_ck) CKS(cudaMemcpyAsync(cell_kind, ck, sizeof(int32_t) * n_cell, cudaMemcpyDeviceToHost, s));
+    if (h_tp) CKS(cudaMemcpyAsync(cell_tri_ptr, tp, sizeof(int64_t) * (n_cell + 1), cudaMemcpyDeviceToHost, s));
+    if (h_xy) CKS(cudaMemcpyAsync(tri_xy, txy, sizeof(double) * 6 * n_tri, cudaMemcpyDeviceToHost, s));
+    if (h_rho) CKS(cudaMemcpyAsync(tri_rho, trho, sizeof(double) * 3 * n_tri * n_mesh, cudaMemcpyDeviceToHost, s));
+    CKS(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CKS(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+#undef CKS
+    free_pool(ctx, tmp);
+    if (kernel_ms) *kernel_ms = ms;
+    return MOFEM_OK;
+}
+
 int mofem_set_profile(mofem_ctx *ctx, int on)
 {
     if (!ctx) return MOFEM_E_ARG;

@@ -107,6 +107,11 @@ cudaError_t rho_run(int64_t n_vert, int n_mesh, const double *vert_xy, const int
                     const int32_t *elem_nv, const double *elem_xy, const double *elem_w, double *rho, int *err,
                     unsigned long long *newton_total, cudaStream_t s);
 
+// overlay.cu
+void overlay_sizes(int nx, int ny, int b_lo, int b_hi, int n_mesh, int64_t out[5]);
+cudaError_t overlay_run(int nx, int ny, int b_lo, int b_hi, int n_mesh, const double *X0, const double *X1, int32_t *cell_elem,
+                        int32_t *cell_kind, int64_t *cell_tri_ptr, double *tri_xy, double *tri_rho, cudaStream_t s);
+
 // pcg.cu
 struct DevSystem {
     int64_t n;            // local scalar unknowns (2 * local nodes, ghosts included)

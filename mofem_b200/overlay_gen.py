@@ -441,6 +441,61 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     return out + (pm,) if return_meshes else out
 
 
+def patch_family_gpu(ctx, n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
+                     solver: int = SOLVER_LOWER, ny: int = None, patch_rows=None, n_mesh: int = 2, to_host: bool = False):
+    """:func:`patch_family` with the overlay built on the GPU (``mofem_overlay_patch_family``, ``csrc/overlay.cu``): the
+    cell and triangle arrays of the returned ``FlatProblem`` are CUDA tensors on the context's device (numpy arrays with
+    ``to_host=True``), bit-identical to the host generator's; node / element tables, right-hand side and constraints are
+    O(nodes) numpy work as before.  Returns ``(FlatProblem, rhs, fixed, fixed_value, kernel_ms)``."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    if n_mesh not in (2, 3):
+        raise ValueError("n_mesh must be 2 or 3")
+    pm = patch_meshes(n0, jitter, seed, ny)
+    nx, ny = pm.nx, pm.ny
+    Px, Py = pm.Px, pm.Py
+    b_lo, b_hi = (0, Py) if patch_rows is None else (int(patch_rows[0]), int(patch_rows[1]))
+    if not (0 <= b_lo < b_hi <= Py):
+        raise ValueError("patch_rows out of range")
+    L = _lib.load()
+    sz = (C.c_int64 * 5)()
+    _lib.raise_for(L.mofem_overlay_patch_sizes(nx, ny, b_lo, b_hi, n_mesh, sz), ctx._h)
+    n_tri, n_cell = int(sz[3]), int(sz[4])
+    dev = torch.device("cuda", ctx.device)
+    out = dict(cell_elem=torch.empty((n_cell, n_mesh), dtype=torch.int32, device=dev),
+               cell_kind=torch.empty(n_cell, dtype=torch.int32, device=dev),
+               cell_tri_ptr=torch.empty(n_cell + 1, dtype=torch.int64, device=dev),
+               tri_xy=torch.empty((n_tri, 3, 2), dtype=torch.float64, device=dev),
+               tri_rho=torch.empty((n_tri, 3, n_mesh), dtype=torch.float64, device=dev))
+    X0 = np.ascontiguousarray(pm.X0); X1 = np.ascontiguousarray(pm.X1)
+    ms = C.c_double(0.0)
+    _lib.raise_for(L.mofem_overlay_patch_family(ctx._h, nx, ny, b_lo, b_hi, n_mesh, _lib.ptr(X0), _lib.ptr(X1),
+                                                _lib.ptr(out["cell_elem"]), _lib.ptr(out["cell_kind"]),
+                                                _lib.ptr(out["cell_tri_ptr"]), _lib.ptr(out["tri_xy"]), _lib.ptr(out["tri_rho"]),
+                                                C.byref(ms)), ctx._h)
+    if to_host:
+        out = {k: v.cpu().numpy() for k, v in out.items()}
+    n_elem0 = pm.n_elem0
+    elem_nodes = np.full((pm.n_elem, 9), -1, dtype=np.int32)
+    elem_nodes[:n_elem0, :4] = pm.elem_nodes0()
+    elem_nodes[n_elem0:, :4] = pm.elem_nodes1()
+    fp = FlatProblem(
+        solver=int(solver), n_mesh=n_mesh, node_xy=np.ascontiguousarray(pm.node_xy()), elem_nodes=elem_nodes,
+        elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
+        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.repeat(_patch_mesh_ids(Px, Py, n_mesh), 25)]),
+        mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem], **out)
+    n_dof = 2 * pm.n_node
+    fixed = np.zeros(n_dof, dtype=np.uint8)
+    left = np.arange(ny + 1) * (nx + 1)
+    fixed[2 * left] = 1; fixed[2 * left + 1] = 1
+    rhs = np.zeros(n_dof)
+    rhs[2 * nx] = 1.0; rhs[2 * nx + 1] = -0.5
+    return fp, rhs, fixed, np.zeros(n_dof), float(ms.value)
+
+
 def _patch_mesh_ids(Px, Py, n_mesh):
     """Mesh id of every patch, patch-major order (b * Px + a)."""
     b, a = np.meshgrid(np.arange(Py), np.arange(Px), indexing="ij")

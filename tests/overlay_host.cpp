@@ -1,0 +1,30 @@
+// Host build of mofem_b200/csrc/overlay_core.h (the SAME source the CUDA kernels of overlay.cu compile) so that its
+// arithmetic can be compared bit for bit with the NumPy generator on a machine without a GPU (tests/test_overlay_core.py).
+//   g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC tests/overlay_host.cpp -o tests/build/liboverlay_host.so
+#include "../mofem_b200/csrc/overlay_core.h"
+
+using namespace mofem_ovl;
+
+extern "C" void ovl_host_sizes(int nx, int ny, int b_lo, int b_hi, int n_mesh, int64_t *out)
+{
+    const Layout L = make_layout(nx, ny, b_lo, b_hi, n_mesh);
+    out[0] = L.n_reg; out[1] = L.n_ring; out[2] = L.n_piece; out[3] = L.n_tri;
+}
+
+extern "C" void ovl_host_generate(int nx, int ny, int b_lo, int b_hi, int n_mesh, const double *X0, const double *X1,
+                                  int32_t *cell_elem, int32_t *cell_kind, int64_t *cell_tri_ptr, double *tri_xy, double *tri_rho)
+{
+    const Layout L = make_layout(nx, ny, b_lo, b_hi, n_mesh);
+    const Meshes m{nx, ny, L.Px, L.Py, X0, X1};
+    const Outputs o{cell_elem, cell_kind, cell_tri_ptr, tri_xy, tri_rho};
+    for (int b = b_lo; b < b_hi; b++)
+        for (int a = 0; a < L.Px; a++) {
+            for (int q = 0; q < 5; q++)
+                for (int p = 0; p < 5; p++) gen_patch_element(m, L, o, b, a, q, p);
+            for (int r = 0; r < RING_CELLS; r++) gen_ring_cell(m, L, o, b, a, r);
+        }
+    const int j0 = PERIOD * b_lo - 1 > 0 ? PERIOD * b_lo - 1 : 0, j1 = PERIOD * b_hi;
+    for (int j = j0; j < j1; j++)
+        for (int i = 0; i < nx; i++) gen_regular(L, o, j, i, untouched_before_row(j, nx) - untouched_before_row(j0, nx));
+    cell_tri_ptr[L.n_cell()] = L.n_tri;
+}

@@ -1,0 +1,92 @@
+"""Overlay of the structured patch family by pairwise convex clipping (csrc/overlay_core.h + overlay.cu).
+
+CPU: the header the CUDA kernels compile is built with the host compiler (tests/overlay_host.cpp, -ffp-contract=off) and
+compared BIT FOR BIT with the NumPy generator mofem_b200/overlay_gen.py -- which tests/test_overlay_gen.py pins against the
+reference's own plane sweep / rhoCalculation / triangulation (fixtures patch16, patch16_m3).
+GPU: the kernels, through the C-ABI, against the same generator."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+from mofem_b200 import overlay_gen
+
+ARRAYS = ("cell_elem", "cell_kind", "cell_tri_ptr", "tri_xy", "tri_rho")
+CASES = [dict(n0=16), dict(n0=16, n_mesh=3), dict(n0=24, ny=16), dict(n0=16, ny=32, patch_rows=(1, 3)),
+         dict(n0=64, ny=32, patch_rows=(2, 4), n_mesh=3), dict(n0=96, jitter=0.2), dict(n0=32, jitter=0.0)]
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.int64) if a.dtype == np.float64 else a
+
+
+def _host_lib():
+    src = os.path.join(REPO, "tests", "overlay_host.cpp")
+    hdr = os.path.join(REPO, "mofem_b200", "csrc", "overlay_core.h")
+    so = os.path.join(REPO, "tests", "build", "liboverlay_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so])
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_host_build_of_the_kernel_source_is_bit_identical_to_the_generator(case):
+    L = _host_lib()
+    fp, _, _, _, pm = overlay_gen.patch_family(return_meshes=True, **case)
+    n_mesh = case.get("n_mesh", 2)
+    b_lo, b_hi = case.get("patch_rows", (0, pm.Py))
+    sz = (C.c_int64 * 4)()
+    L.ovl_host_sizes(pm.nx, pm.ny, b_lo, b_hi, n_mesh, sz)
+    n_reg, n_ring, n_piece, n_tri = list(sz)
+    n_cell = n_reg + n_ring + n_piece
+    assert (n_cell, n_tri) == (fp.n_cell, fp.n_tri)
+    out = dict(cell_elem=np.empty((n_cell, n_mesh), np.int32), cell_kind=np.empty(n_cell, np.int32),
+               cell_tri_ptr=np.empty(n_cell + 1, np.int64), tri_xy=np.empty((n_tri, 3, 2)), tri_rho=np.empty((n_tri, 3, n_mesh)))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    X0 = np.ascontiguousarray(pm.X0); X1 = np.ascontiguousarray(pm.X1)
+    L.ovl_host_generate(pm.nx, pm.ny, b_lo, b_hi, n_mesh, p(X0), p(X1), *[p(out[k]) for k in ARRAYS])
+    for k in ARRAYS:
+        assert np.array_equal(_bits(out[k]), _bits(getattr(fp, k))), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES + [dict(n0=256)], ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_gpu_overlay_is_bit_identical_to_the_generator(gpu_ctx, case):
+    fp, rhs, fixed, val = overlay_gen.patch_family(**case)
+    g, rhs_g, fixed_g, val_g, ms = overlay_gen.patch_family_gpu(gpu_ctx, to_host=True, **case)
+    for k in ARRAYS:
+        assert np.array_equal(_bits(getattr(g, k)), _bits(getattr(fp, k))), k
+    for k in ("node_xy", "elem_nodes", "elem_nn", "elem_mat", "elem_mesh", "mat_D"):
+        assert np.array_equal(getattr(g, k), getattr(fp, k)), k
+    assert np.array_equal(rhs, rhs_g) and np.array_equal(fixed, fixed_g) and np.array_equal(val, val_g)
+
+
+@pytest.mark.gpu
+def test_gpu_overlay_feeds_the_solver_from_device_memory(gpu_ctx):
+    """Device-resident overlay arrays go straight into mofem_set_problem (zero-copy); same matrix as from the host arrays."""
+    fp, rhs, fixed, val = overlay_gen.patch_family(64)
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    ref = gpu_ctx.csr()
+    g, rhs_g, fixed_g, val_g, _ = overlay_gen.patch_family_gpu(gpu_ctx, 64)
+    gpu_ctx.set_problem(g).symbolic().assemble()
+    got = gpu_ctx.csr()
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    gpu_ctx.set_system(rhs_g, fixed_g, val_g)
+    u, info = gpu_ctx.solve(rtol=1e-10)
+    assert info["converged"] == 1
+
+
+@pytest.mark.gpu
+def test_gpu_overlay_argument_errors(gpu_ctx):
+    from mofem_b200 import _lib
+    L = _lib.load()
+    sz = (C.c_int64 * 5)()
+    assert L.mofem_overlay_patch_sizes(12, 16, 0, 2, 2, sz) == _lib.E_ARG        # nx not a multiple of 8
+    assert L.mofem_overlay_patch_sizes(16, 16, 1, 1, 2, sz) == _lib.E_ARG        # empty row range
+    assert L.mofem_overlay_patch_sizes(16, 16, 0, 2, 4, sz) == _lib.E_ARG        # n_mesh
+    assert L.mofem_overlay_patch_sizes(16, 16, 0, 2, 2, sz) == 0 and sz[4] == 592
