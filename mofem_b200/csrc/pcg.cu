@@ -1014,12 +1014,9 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w_in, 
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         ring_on = max_deg <= (unsigned int)PcgRing::MAXDEG;
         if (ring_on) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                if ((e = cudaFuncSetAttribute(k_spmv_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(k_spmv_ring_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
-                attr_set = true;
-            }
+            // per device (a process may hold contexts on several GPUs), so set on every solve: microseconds
+            if ((e = cudaFuncSetAttribute(k_spmv_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(k_spmv_ring_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
         }
     }
     // fused update + direction kernel: needs all its CTAs co-resident (software grid barrier)
