@@ -116,3 +116,27 @@ def test_default_path_is_bit_reproducible(gpu_ctx):
         u, info = gpu_ctx.solve(rtol=1e-10)
         outs.append((u.copy(), info["iterations"]))
     assert all(np.array_equal(outs[0][0], o[0]) and o[1] == outs[0][1] for o in outs[1:])
+
+
+def test_ring_tiles_without_any_sub_block(gpu_ctx):
+    """Thousands of nodes no element touches (empty node rows, like the None mid-nodes of the reference's decks): whole ring
+    tiles then carry row pointers only.  The solution on the used nodes must not change."""
+    fp = _fan(60)
+    n_used = fp.n_node
+    extra = 5000
+    fp2 = _fan(60)
+    fp2.node_xy = np.vstack([fp.node_xy, np.full((extra, 2), np.nan)])
+    sols = []
+    for prob in (fp, fp2):
+        n = prob.n_dof
+        fixed = np.zeros(n, np.uint8); val = np.zeros(n)
+        fixed[2:6] = 1
+        fixed[2 * n_used:] = 1                      # DOFs of unused nodes: the reference's spsolve would be singular otherwise
+        rhs = np.zeros(n); rhs[2 * 30 + 1] = -1.0; rhs[0] = 0.5
+        gpu_ctx.set_problem(prob).symbolic().assemble()
+        gpu_ctx.set_system(rhs, fixed, val)
+        u, info = gpu_ctx.solve(rtol=1e-12, maxit=100000)
+        assert info["converged"] in (1, 2)
+        sols.append(u[:2 * n_used].copy())
+        assert np.all(u[2 * n_used:] == 0.0)
+    assert np.abs(sols[0] - sols[1]).max() <= 1e-10 * np.abs(sols[0]).max()
