@@ -125,6 +125,35 @@ def algorithmic_bytes(info, n_dof):
     }
 
 
+FP64_PEAK_TFLOPS = 37.2     # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (ncu: 9472 DFMA thread-inst/clk peak)
+
+
+def integration_flops(fp, info, ms):
+    """fp64 roofline of the integration kernels with SURVEY.md section 8d's flop model for quad4 overlays: per evaluation
+    87 k + 167 (k Newton updates), per (point, block) contraction 304, regular quad4 element 4 x (95 + 304).
+    ``algorithmic`` counts ONE evaluation per (point, incident element) -- the minimum; ``executed`` counts what the
+    thread-per-block kernels (like the reference) do: the off-diagonal block re-evaluates both elements."""
+    ce = np.asarray(fp.cell_elem)
+    m = (ce >= 0).sum(1)
+    tri = np.diff(np.asarray(fp.cell_tri_ptr))
+    overlay = np.asarray(fp.cell_kind) == 1
+    points = 6 * tri[overlay]                                   # 6-point rule for quad4 x quad4 (stiffnessMatrix.py:104-106)
+    mo = m[overlay]
+    evals_min = float((points * mo).sum())
+    evals_done = float((points * mo * mo).sum())
+    contractions = float((points * mo * (mo + 1) // 2).sum())
+    kbar = info["newton_updates"] / max(info["n_eval"], 1)
+    f_eval = 87.0 * kbar + 167.0
+    regular = float((~overlay).sum()) * 4 * (95 + 304)
+    alg = evals_min * f_eval + contractions * 304 + regular
+    done = evals_done * f_eval + contractions * 304 + regular
+    return {"newton_updates_per_evaluation": kbar, "algorithmic_gflop": alg / 1e9, "executed_gflop": done / 1e9,
+            "algorithmic_tflops": alg / (ms * 1e-3) / 1e12, "executed_tflops": done / (ms * 1e-3) / 1e12,
+            "fp64_peak_tflops": FP64_PEAK_TFLOPS, "frac_fp64_algorithmic": alg / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+            "frac_fp64_executed": done / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+            "evaluations_model": evals_done}
+
+
 def run_reference(args):
     """The reference's CPU algorithm (oracle port, all host threads) + scipy coo->csr + spsolve, on a bounded sample."""
     import scipy.sparse as sp
@@ -440,6 +469,7 @@ def main():
     im = phases["integrate_ms"] / args.steps
     kernels["integrate (all classes)"] = {"ms": im, "cells_per_s": fp.n_cell / (im * 1e-3),
                                           "newton_updates": info["newton_updates"], "evaluations": info["n_eval"]}
+    kernels["integrate (all classes)"].update(integration_flops(fp, info, im))
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
