@@ -237,7 +237,8 @@ def main():
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
     ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
     ap.add_argument("--host-overlay", action="store_true",
-                    help="1 GPU: build the overlay with the NumPy generator instead of the CUDA one (same bits; untimed either way)")
+                    help="build the overlay with the NumPy generator instead of the CUDA kernels (1 GPU) / their host build (N > 1 strips); "
+                         "same bits, untimed either way")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: ONE n0 x n0 problem cut into N strips (BASELINE configs 4 and 5) instead of a stack of N blocks "
                          "of n0 x n0 (weak scaling, the default); n0 / 8 must be a multiple of N")
@@ -266,7 +267,8 @@ def main():
     # ---- untimed preprocessing: the flattened overlay (what the plane sweep + flatten() hand to the solver) ------
     # N > 1 (weak scaling): the domain is a stack of N blocks of n0 x n0 mesh-0 elements; rank r owns block r (its
     # mesh-0 node rows and the patches inside) and generates only the cells that touch its nodes.
-    # (Generation forks worker processes, so it runs before any CUDA / NCCL initialisation.)
+    # Strips come from the overlay core built for the host (liboverlay_host.so: the source of the CUDA overlay kernels, same
+    # bits as the NumPy generator, no forked workers), before CUDA / NCCL are initialised; --host-overlay: NumPy generator.
     t0 = time.perf_counter()
     part = None
     n_cells_global = None
@@ -290,7 +292,8 @@ def main():
         else:
             ny, per = args.n0 * world, px                  # a stack of N blocks of n0 x n0
         rows_per_rank = 8 * per
-        strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per), n_mesh=args.meshes)
+        strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per), n_mesh=args.meshes,
+                                                    engine="numpy" if args.host_overlay else "native")
         n_node0 = (args.n0 + 1) * (ny + 1)
         owner = np.empty(strip.n_node, np.int32)
         owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // rows_per_rank, world - 1)
@@ -505,7 +508,8 @@ def main():
         "energy": last["energy"],
         "prep_s": prep_s,
         "overlay": ({"where": "gpu (csrc/overlay.cu, pairwise convex clipping)", "kernels_ms": overlay_ms} if overlay_ms is not None
-                    else {"where": "host (mofem_b200/overlay_gen.py)"}),
+                    else {"where": "host, NumPy generator (mofem_b200/overlay_gen.py)" if args.host_overlay or world == 1
+                          else "host build of the overlay core (liboverlay_host.so), per-rank strips"}),
     }
     emit(out)
     if world > 1:

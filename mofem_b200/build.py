@@ -39,8 +39,24 @@ def _deps():
     return hdr
 
 
+HOST_LIB = os.path.join(HERE, "liboverlay_host.so")
+
+
+def build_host(force=False, verbose=False):
+    """Host build of the overlay core (csrc/overlay_host.cpp): preprocessing without a device + the CPU parity check."""
+    src = os.path.join(CSRC, "overlay_host.cpp")
+    hdr = os.path.join(CSRC, "overlay_core.h")
+    if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", HOST_LIB]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
+    build_host(force, verbose)
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
     newest_hdr = max(os.path.getmtime(h) for h in _deps())
     objs, relink = [], force or not os.path.exists(LIB)

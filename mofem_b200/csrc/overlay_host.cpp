@@ -1,7 +1,10 @@
-// Host build of mofem_b200/csrc/overlay_core.h (the SAME source the CUDA kernels of overlay.cu compile) so that its
-// arithmetic can be compared bit for bit with the NumPy generator on a machine without a GPU (tests/test_overlay_core.py).
-//   g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC tests/overlay_host.cpp -o tests/build/liboverlay_host.so
-#include "../mofem_b200/csrc/overlay_core.h"
+// Host build of overlay_core.h -- the SAME source the CUDA kernels of overlay.cu compile -- as liboverlay_host.so:
+//   * untimed preprocessing where no device is at hand yet (the multi-GPU driver builds each rank's strip before CUDA / NCCL
+//     are initialised): mofem_b200/overlay_gen.py: patch_family(engine="native"), 10x faster than the NumPy generator and
+//     without its forked worker processes;
+//   * the CPU check that the kernel source reproduces the NumPy generator bit for bit (tests/test_overlay_core.py).
+// Built by mofem_b200/build.py:  g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC overlay_host.cpp
+#include "overlay_core.h"
 
 using namespace mofem_ovl;
 

@@ -286,7 +286,7 @@ def _ring_rows_worker(rows):
 
 def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
                  solver: int = SOLVER_LOWER, return_meshes: bool = False, ny: int = None, patch_rows=None,
-                 n_mesh: int = 2):
+                 n_mesh: int = 2, engine: str = "numpy"):
     """Flattened 2-mesh patch-family problem + its linear system.
 
     Returns ``(FlatProblem, rhs, fixed, fixed_value)``: left edge of mesh 0 clamped, concentrated load
@@ -302,12 +302,19 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     stay global, so the result can go straight into :func:`mofem_b200.partition.partition_problem`."""
     if n_mesh not in (2, 3):
         raise ValueError("n_mesh must be 2 or 3")
+    if engine not in ("numpy", "native"):
+        raise ValueError("engine must be 'numpy' or 'native'")
     pm = patch_meshes(n0, jitter, seed, ny)
     nx, ny = pm.nx, pm.ny
     Px, Py = pm.Px, pm.Py
     b_lo, b_hi = (0, Py) if patch_rows is None else (int(patch_rows[0]), int(patch_rows[1]))
     if not (0 <= b_lo < b_hi <= Py):
         raise ValueError("patch_rows out of range")
+    if engine == "native":
+        # the overlay core the CUDA kernels compile, built for the host (csrc/overlay_host.cpp): same bits as below, no
+        # forked workers, ~10x faster -- what the multi-GPU driver uses before CUDA / NCCL are up
+        out = _finish_problem(pm, _native_overlay(pm, b_lo, b_hi, n_mesh), n_mesh, solver, E, nu)
+        return out + (pm,) if return_meshes else out
     X0, X1 = pm.X0, pm.X1
     n_elem0 = pm.n_elem0
     node0 = lambda j, i: j * (nx + 1) + i
@@ -441,6 +448,47 @@ def patch_family(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 100
     return out + (pm,) if return_meshes else out
 
 
+def _native_overlay(pm, b_lo, b_hi, n_mesh):
+    """Cell / triangle arrays from liboverlay_host.so (built by ``python -m mofem_b200.build``)."""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboverlay_host.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -m mofem_b200.build`")
+    L = C.CDLL(path)
+    sz = (C.c_int64 * 4)()
+    L.ovl_host_sizes(C.c_int(pm.nx), C.c_int(pm.ny), C.c_int(b_lo), C.c_int(b_hi), C.c_int(n_mesh), sz)
+    n_cell, n_tri = int(sz[0] + sz[1] + sz[2]), int(sz[3])
+    out = dict(cell_elem=np.empty((n_cell, n_mesh), np.int32), cell_kind=np.empty(n_cell, np.int32),
+               cell_tri_ptr=np.empty(n_cell + 1, np.int64), tri_xy=np.empty((n_tri, 3, 2)), tri_rho=np.empty((n_tri, 3, n_mesh)))
+    X0 = np.ascontiguousarray(pm.X0); X1 = np.ascontiguousarray(pm.X1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.ovl_host_generate(C.c_int(pm.nx), C.c_int(pm.ny), C.c_int(b_lo), C.c_int(b_hi), C.c_int(n_mesh), p(X0), p(X1),
+                        p(out["cell_elem"]), p(out["cell_kind"]), p(out["cell_tri_ptr"]), p(out["tri_xy"]), p(out["tri_rho"]))
+    return out
+
+
+def _finish_problem(pm, cells, n_mesh, solver, E, nu):
+    """(FlatProblem, rhs, fixed, fixed_value) around given cell / triangle arrays: node and element tables, clamped left
+    edge, corner load -- identical to the tail of :func:`patch_family`."""
+    nx, ny, n_elem0 = pm.nx, pm.ny, pm.n_elem0
+    elem_nodes = np.full((pm.n_elem, 9), -1, dtype=np.int32)
+    elem_nodes[:n_elem0, :4] = pm.elem_nodes0()
+    elem_nodes[n_elem0:, :4] = pm.elem_nodes1()
+    fp = FlatProblem(
+        solver=int(solver), n_mesh=n_mesh, node_xy=np.ascontiguousarray(pm.node_xy()), elem_nodes=elem_nodes,
+        elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
+        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.repeat(_patch_mesh_ids(pm.Px, pm.Py, n_mesh), 25)]),
+        mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem], **cells)
+    n_dof = 2 * pm.n_node
+    fixed = np.zeros(n_dof, dtype=np.uint8)
+    left = np.arange(ny + 1) * (nx + 1)
+    fixed[2 * left] = 1; fixed[2 * left + 1] = 1
+    rhs = np.zeros(n_dof)
+    rhs[2 * nx] = 1.0; rhs[2 * nx + 1] = -0.5
+    return fp, rhs, fixed, np.zeros(n_dof)
+
+
 def patch_family_gpu(ctx, n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
                      solver: int = SOLVER_LOWER, ny: int = None, patch_rows=None, n_mesh: int = 2, to_host: bool = False):
     """:func:`patch_family` with the overlay built on the GPU (``mofem_overlay_patch_family``, ``csrc/overlay.cu``): the
@@ -478,22 +526,7 @@ def patch_family_gpu(ctx, n0: int, jitter: float = 0.12, seed: int = SEED, E: fl
                                                 C.byref(ms)), ctx._h)
     if to_host:
         out = {k: v.cpu().numpy() for k, v in out.items()}
-    n_elem0 = pm.n_elem0
-    elem_nodes = np.full((pm.n_elem, 9), -1, dtype=np.int32)
-    elem_nodes[:n_elem0, :4] = pm.elem_nodes0()
-    elem_nodes[n_elem0:, :4] = pm.elem_nodes1()
-    fp = FlatProblem(
-        solver=int(solver), n_mesh=n_mesh, node_xy=np.ascontiguousarray(pm.node_xy()), elem_nodes=elem_nodes,
-        elem_nn=np.full(pm.n_elem, 4, dtype=np.int32), elem_mat=np.zeros(pm.n_elem, dtype=np.int32),
-        elem_mesh=np.concatenate([np.zeros(n_elem0, np.int32), np.repeat(_patch_mesh_ids(Px, Py, n_mesh), 25)]),
-        mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3), n_mesh_regular=0, mesh_offset=[0, n_elem0, pm.n_elem], **out)
-    n_dof = 2 * pm.n_node
-    fixed = np.zeros(n_dof, dtype=np.uint8)
-    left = np.arange(ny + 1) * (nx + 1)
-    fixed[2 * left] = 1; fixed[2 * left + 1] = 1
-    rhs = np.zeros(n_dof)
-    rhs[2 * nx] = 1.0; rhs[2 * nx + 1] = -0.5
-    return fp, rhs, fixed, np.zeros(n_dof), float(ms.value)
+    return _finish_problem(pm, out, n_mesh, solver, E, nu) + (float(ms.value),)
 
 
 def _patch_mesh_ids(Px, Py, n_mesh):

@@ -12,7 +12,7 @@ N0 = 664
 @pytest.fixture(scope="module")
 def big(gpu_ctx):
     from mofem_b200 import overlay_gen
-    fp, rhs, fixed, val = overlay_gen.patch_family(N0)
+    fp, rhs, fixed, val = overlay_gen.patch_family(N0, engine="native")   # no forked workers inside a process that holds a CUDA context
     gpu_ctx.clear_halo()
     gpu_ctx.set_problem(fp).symbolic().assemble()
     return fp, rhs, fixed, val

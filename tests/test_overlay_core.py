@@ -1,17 +1,14 @@
 """Overlay of the structured patch family by pairwise convex clipping (csrc/overlay_core.h + overlay.cu).
 
-CPU: the header the CUDA kernels compile is built with the host compiler (tests/overlay_host.cpp, -ffp-contract=off) and
-compared BIT FOR BIT with the NumPy generator mofem_b200/overlay_gen.py -- which tests/test_overlay_gen.py pins against the
+CPU: the header the CUDA kernels compile is built with the host compiler (csrc/overlay_host.cpp -> liboverlay_host.so,
+-ffp-contract=off) and compared BIT FOR BIT with the NumPy generator mofem_b200/overlay_gen.py -- which tests/test_overlay_gen.py pins against the
 reference's own plane sweep / rhoCalculation / triangulation (fixtures patch16, patch16_m3).
 GPU: the kernels, through the C-ABI, against the same generator."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import REPO
 from mofem_b200 import overlay_gen
 
 ARRAYS = ("cell_elem", "cell_kind", "cell_tri_ptr", "tri_xy", "tri_rho")
@@ -25,13 +22,8 @@ def _bits(a):
 
 
 def _host_lib():
-    src = os.path.join(REPO, "tests", "overlay_host.cpp")
-    hdr = os.path.join(REPO, "mofem_b200", "csrc", "overlay_core.h")
-    so = os.path.join(REPO, "tests", "build", "liboverlay_host.so")
-    os.makedirs(os.path.dirname(so), exist_ok=True)
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so])
-    return C.CDLL(so)
+    from mofem_b200 import build
+    return C.CDLL(build.build_host())
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
@@ -52,6 +44,19 @@ def test_host_build_of_the_kernel_source_is_bit_identical_to_the_generator(case)
     L.ovl_host_generate(pm.nx, pm.ny, b_lo, b_hi, n_mesh, p(X0), p(X1), *[p(out[k]) for k in ARRAYS])
     for k in ARRAYS:
         assert np.array_equal(_bits(out[k]), _bits(getattr(fp, k))), k
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_native_engine_of_patch_family_is_bit_identical(case):
+    """``patch_family(engine="native")`` (what the multi-GPU driver uses for its strips) against the NumPy engine: every
+    array of the problem and the linear system."""
+    a = overlay_gen.patch_family(**case)
+    b = overlay_gen.patch_family(engine="native", **case)
+    for k in a[0].ARRAYS:
+        x, y = getattr(a[0], k), getattr(b[0], k)
+        assert (x is None and y is None) or (x.dtype == y.dtype and x.shape == y.shape and np.array_equal(_bits(x), _bits(y))), k
+    assert (a[0].solver, a[0].n_mesh, a[0].mesh_offset) == (b[0].solver, b[0].n_mesh, b[0].mesh_offset)
+    assert all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
 
 
 @pytest.mark.gpu

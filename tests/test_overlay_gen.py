@@ -16,10 +16,12 @@ def _canon_tris(t):
 import pytest
 
 
+@pytest.mark.parametrize("engine", ["numpy", "native"])
 @pytest.mark.parametrize("name,n_mesh", [("patch16", 2), ("patch16_m3", 3)])
-def test_generator_reproduces_the_reference_overlay(name, n_mesh):
+def test_generator_reproduces_the_reference_overlay(name, n_mesh, engine):
+    """Both engines (NumPy; the overlay core of the CUDA kernels built for the host) against the reference's own plane sweep."""
     fpr, d = load_golden(name)
-    fp, rhs, fixed, val = overlay_gen.patch_family(16, n_mesh=n_mesh)
+    fp, rhs, fixed, val = overlay_gen.patch_family(16, n_mesh=n_mesh, engine=engine)
     assert fp.n_mesh == fpr.n_mesh == n_mesh
     assert np.array_equal(fp.node_xy, fpr.node_xy)
     assert fp.n_cell == fpr.n_cell and fp.n_tri == fpr.n_tri

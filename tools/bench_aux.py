@@ -66,7 +66,7 @@ out["rho"] = {"vertices": V, "meshes": 2, "newton_updates": nw, "kernel_ms": k_m
               "parity": "bit-identical to the oracle on the sample"}
 
 # ---- sampler ----------------------------------------------------------------------------------------------------
-fp, rhs, fixed, val = patch_family(n0)
+fp, rhs, fixed, val = patch_family(n0, engine="native")
 for k in FlatProblem.ARRAYS:
     a = getattr(fp, k)
     if a is not None and k != "elem_mesh":

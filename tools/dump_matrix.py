@@ -11,7 +11,7 @@ from mofem_b200.overlay_gen import patch_family
 n0 = int(sys.argv[1]) if len(sys.argv) > 1 else 664
 out = sys.argv[2] if len(sys.argv) > 2 else "/tmp/spmv_lab"
 os.makedirs(out, exist_ok=True)
-fp, rhs, fixed, val = patch_family(n0)
+fp, rhs, fixed, val = patch_family(n0, engine="native")
 ctx = Context(0)
 ctx.set_problem(fp).symbolic().assemble()
 indptr, indices, data = ctx.csr()

@@ -18,7 +18,7 @@ pos = [a for a in sys.argv[1:] if "=" not in a]
 kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
 n0 = int(pos[0]) if len(pos) > 0 else 664
 iters = int(pos[1]) if len(pos) > 1 else 20
-fp, rhs, fixed, val = patch_family(n0)
+fp, rhs, fixed, val = patch_family(n0, engine="native")
 dev = torch.device("cuda", 0)
 for k in FlatProblem.ARRAYS:
     a = getattr(fp, k)
