@@ -1,6 +1,9 @@
 """One-screen digest of a bench.py JSON line:  python tools/show_bench.py <file.json>"""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # quiet under `| head`
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("value", round(d["value"]), d["unit"], "| ms/step", round(d["ms_per_step"], 1), "| e2e", round(d["e2e"]["value"]), "| gpus", d["n_gpus"],
