@@ -31,3 +31,16 @@ extern "C" void ovl_host_generate(int nx, int ny, int b_lo, int b_hi, int n_mesh
         for (int i = 0; i < nx; i++) gen_regular(L, o, j, i, untouched_before_row(j, nx) - untouched_before_row(j0, nx));
     cell_tri_ptr[L.n_cell()] = L.n_tri;
 }
+
+// test hook: the ear rule alone on one polygon of n <= 6 vertices (pts [n][2]); returns the triangle count
+extern "C" int ovl_host_ear(const double *pts, int n, int32_t *tri_out)
+{
+    if (n < 3 || n > EAR_MAX) return -1;
+    P2 p[EAR_MAX];
+    for (int k = 0; k < n; k++) p[k] = P2{pts[2 * k], pts[2 * k + 1]};
+    int tri[EAR_MAX - 2][3];
+    const int nt = ear_triangulate(p, n, tri);
+    for (int t = 0; t < nt; t++)
+        for (int v = 0; v < 3; v++) tri_out[3 * t + v] = tri[t][v];
+    return nt;
+}

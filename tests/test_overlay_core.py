@@ -95,3 +95,29 @@ def test_gpu_overlay_argument_errors(gpu_ctx):
     assert L.mofem_overlay_patch_sizes(16, 16, 1, 1, 2, sz) == _lib.E_ARG        # empty row range
     assert L.mofem_overlay_patch_sizes(16, 16, 0, 2, 4, sz) == _lib.E_ARG        # n_mesh
     assert L.mofem_overlay_patch_sizes(16, 16, 0, 2, 2, sz) == 0 and sz[4] == 592
+
+
+def test_ear_rule_matches_the_python_restatement_on_random_polygons():
+    """The C++ ear rule (explicit stack) against overlay_gen.ear_triangulate (the restatement of the reference's recursive
+    simpleTriangulation that tests/test_overlay_gen.py checks) on random star-shaped polygons with reflex vertices."""
+    L = _host_lib()
+    rng = np.random.default_rng(7)
+    n_reflex_cases = 0
+    for trial in range(3000):
+        n = int(rng.integers(3, 7))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        if np.min(np.diff(np.concatenate([ang, [ang[0] + 2 * np.pi]]))) < 0.15:
+            continue
+        rad = rng.uniform(0.25, 1.0, n)                           # star-shaped around the origin: simple, often non-convex
+        pts = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1) + rng.uniform(-3, 3, 2)
+        if trial % 5 == 0:                                        # some exactly horizontal edges / equal heights
+            pts[1, 1] = pts[0, 1]
+        want = overlay_gen.ear_triangulate([tuple(p) for p in pts.tolist()])
+        out = np.zeros(12, np.int32)
+        nt = L.ovl_host_ear(np.ascontiguousarray(pts).ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        assert nt == len(want) == n - 2
+        assert [tuple(t) for t in out[:3 * nt].reshape(-1, 3).tolist()] == [tuple(t) for t in want], (trial, pts)
+        e1, e2 = np.roll(pts, -1, 0) - pts, np.roll(pts, -2, 0) - np.roll(pts, -1, 0)
+        cross = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+        n_reflex_cases += int((cross < 0).any())
+    assert n_reflex_cases > 500
