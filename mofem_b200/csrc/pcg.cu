@@ -5,15 +5,20 @@
 // search directions are zero on fixed DOFs and the SpMV zeroes fixed rows, so the iteration is exactly CG on the
 // reduced free-free system without building a second matrix.
 //
-// SpMV reads the scalar CSR values through the node-level pattern (one column index per 2x2 sub-block:
-// 9 bytes per stored scalar instead of 12).  8 lanes share a node row, every lane issues up to 4 independent
-// {index, 2 x 16-byte value, 16-byte x gather} groups before the first FMA (rows have 4..34 sub-blocks), the
-// matrix is streamed with evict-first loads so that the vectors stay in L2.  Tuned with tools/spmv_lab.cu:
-// 84 % of the measured copy bandwidth on the 1 M-cell bench matrix.
+// The matrix is the scalar CSR viewed at node level (one column index per 2x2 sub-block: 9 bytes per stored scalar
+// instead of 12).  Two SpMV kernels read it:
+//   k_spmv_ring (spmv_ring.cuh)  the SpMV of the PCG loop: a producer warp streams row tiles into a shared-memory ring with
+//                                cp.async.bulk (TMA), consumer warps multiply out of shared memory; 86 % of the measured
+//                                copy bandwidth on the 1 M-cell bench matrix; _p2p variant with the NVLink halo exchange
+//   k_spmv                       row kernel (8 lanes per node row chase pointer -> {index, values} -> x through global
+//                                loads, 4 independent load groups per lane, evict-first streaming): mofem_spmv, residual
+//                                checks, energy, the NCCL transport, rows too long for a ring stage
+// The vector part of an iteration is ONE kernel (k_pcg_fused: r -= alpha q, dots, grid barrier, x += alpha p,
+// p = z + beta p); on a single GPU the kernels are chained with programmatic dependent launch.
 //
-// Dot products are two-stage with a fixed reduction order (bit-reproducible): every block writes a partial, the
-// last block to finish sums the partials in index order and publishes the scalar.  alpha/beta live on the
-// device; the host only polls the residual every PCG_CHUNK iterations.
+// Dot products have a fixed reduction order (bit-reproducible): per-thread sums over a static assignment, per-CTA
+// partials summed in index order (by the last CTA to finish, or by every CTA after the grid barrier).  alpha/beta live on
+// the device; the host only polls the residual every PCG_CHUNK iterations.
 #include <algorithm>
 
 #include "common.cuh"
