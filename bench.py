@@ -114,12 +114,11 @@ def algorithmic_bytes(info, n_dof):
     n_contrib = info["n_coo"] // 4
     return {
         # block CSR as stored: 8 B per value + one 4 B column index per 2x2 block + node_ptr + x, y + fixed mask
-        "spmv": 8 * nnz + nnz + 8 * (n_node + 1) + 8 * n_dof + 8 * n_dof + n_dof,
+        # + r and dinv of the produced rows (the sums of the single-reduction PCG are taken inside the SpMV)
+        "spmv": 8 * nnz + nnz + 8 * (n_node + 1) + 8 * n_dof + 8 * n_dof + n_dof + 16 * n_dof,
         # SURVEY.md section 8d scalar-CSR figure for the same product (12 B per stored entry)
         "spmv_scalar_csr": 12 * nnz + 4 * (n_dof + 1) + 16 * n_dof,
-        "update": 8 * n_dof * 7,         # reads p, q, x, r, dinv; writes x, r
-        "direction": 8 * n_dof * 4,      # reads r, dinv, p; writes p
-        "fused": 8 * n_dof * 8,          # single GPU, one kernel: reads q, r, dinv, p, x; writes r, x, p
+        "vec": 8 * n_dof * 8,            # k_pcg_vec: reads q, r, dinv, p, x; writes r, x, p
         # numeric reduce: every block value once (32 B per node pair), its 4 B source slot, CSR values out
         "numeric": 32 * n_pair + 4 * n_contrib + 8 * nnz,
     }
@@ -381,7 +380,7 @@ def main():
     sampler.start()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     phases = {"symbolic_ms": 0.0, "integrate_ms": 0.0, "numeric_ms": 0.0, "solve_ms": 0.0}
-    prof = {"spmv_ms": 0.0, "update_ms": 0.0, "direction_ms": 0.0, "iterations": 0}
+    prof = {"spmv_ms": 0.0, "vec_ms": 0.0, "iterations": 0}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
@@ -398,7 +397,7 @@ def main():
     clocks = sampler.stop()
     if prof["iterations"]:
         log(f"[rank {rank}] per-iteration us: spmv {prof['spmv_ms'] / prof['iterations'] * 1e3:.1f} "
-            f"update {prof['update_ms'] / prof['iterations'] * 1e3:.1f} direction {prof['direction_ms'] / prof['iterations'] * 1e3:.1f}")
+            f"vector kernel {prof['vec_ms'] / prof['iterations'] * 1e3:.1f}")
     step_ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
         t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
@@ -457,15 +456,9 @@ def main():
                     "launches_timed": prof["iterations"], "sampled_every": (0 if args.no_profile else max(1, args.profile_every))}
     kernels = {}
     if prof["iterations"]:
-        if prof["direction_ms"] < 0.3 * prof["update_ms"]:      # update + direction ran as one kernel (barrier in between)
-            ms = (prof["update_ms"] + prof["direction_ms"]) / iters
-            kernels["k_pcg_fused"] = {"avg_launch_ms": ms, "gbs": ab["fused"] / (ms * 1e-3) / 1e9,
-                                      "frac_hbm": ab["fused"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-        else:
-            for name in ("update", "direction"):
-                ms = prof[name + "_ms"] / iters
-                kernels["k_pcg_" + name] = {"avg_launch_ms": ms, "gbs": ab[name] / (ms * 1e-3) / 1e9,
-                                            "frac_hbm": ab[name] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        ms = prof["vec_ms"] / iters
+        kernels["k_pcg_vec"] = {"avg_launch_ms": ms, "gbs": ab["vec"] / (ms * 1e-3) / 1e9,
+                                "frac_hbm": ab["vec"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     nm = phases["numeric_ms"] / args.steps
     kernels["k_numeric"] = {"avg_launch_ms": nm, "gbs": ab["numeric"] / (nm * 1e-3) / 1e9,
                             "frac_hbm": ab["numeric"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"]}

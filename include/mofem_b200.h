@@ -91,7 +91,8 @@ typedef struct {
 typedef struct {
     int32_t iterations;
     int32_t converged;    /* 0 no; 1 true residual <= rtol; 2 recurrence residual <= rtol and the true residual
-                             stagnated at the fp64 attainable accuracy (reported in relres_true) */
+                             stagnated at the fp64 attainable accuracy (reported in relres_true), below
+                             max(rtol, "floor_rtol_1e12" option = 1e-8) -- a stagnation above that bound is 0 */
     double relres_true;   /* ||b-Ax|| / ||b|| recomputed at exit */
     double relres_rec;    /* recurrence residual at exit */
     int32_t restarts;     /* times the true residual replaced the recurrence residual */
@@ -195,12 +196,14 @@ int mofem_overlay_patch_family(mofem_ctx *ctx, int32_t nx, int32_t ny, int32_t b
                                double *tri_rho, double *kernel_ms);
 
 /* Per-kernel profile of the PCG loop: on = 1 records CUDA events around the kernels of every iteration of mofem_solve on the
- * context's stream, on = N > 1 around those of every N-th iteration (the others keep their launch overlap), 0 = off.  ms[0..2] = summed device time of the SpMV / update (x,r,dots) / direction (p)
- * kernels of the last mofem_solve, *iterations = iterations profiled. */
+ * context's stream, on = N > 1 around those of every N-th iteration (the others keep their launch overlap), 0 = off.  ms[0..1] = summed device time of the SpMV (incl. halo exchange and the
+ * all-reduce when row-partitioned) / the vector kernel over the sampled iterations of the last mofem_solve, ms[2] = 0,
+ * *iterations = iterations profiled. */
 int mofem_set_profile(mofem_ctx *ctx, int on);
 /* Tuning switches (defaults in brackets): "spmv_ring" [1] PCG SpMV streams the matrix through shared memory with the TMA
- * (0: row kernel); "fused_vec" [1] update + direction of a PCG iteration as one kernel; "pdl" [1] programmatic dependent launch
- * between the PCG kernels (single GPU, with the ring); "l2_persist" [0] / "l2_window" [5] L2 persistence window over the first
+ * (0: row kernel); "pdl" [1] programmatic dependent launch between the two kernels of a PCG iteration (single GPU and peer
+ * transport, with the ring); "floor_rtol_1e12" [10000] = 1e12 x the largest TRUE relative residual mofem_solve still accepts
+ * (converged = 2) when restarts no longer reduce it -- above max(rtol, that) the solve returns MOFEM_E_NOCONV; "l2_persist" [0] / "l2_window" [5] L2 persistence window over the first
  * N PCG vectors during mofem_solve (measured neutral at 1 M cells, harmful at 10 M); "cell_kernel" [0] sends quad4 overlay
  * cells to the warp-cooperative cell kernel instead of the thread-per-block kernels (bit-identical results, measured slower on
  * B200 -- see DESIGN.md; set before mofem_symbolic). */

@@ -39,8 +39,8 @@ struct mofem_ctx {
     bool slab_in_xbuf = false;
     int l2_persist = 0;   // L2 persistence window over the PCG vectors: neutral at 1 M cells since the matrix stream carries evict-first hints, costs 20 % at 10 M (measured) -> off
     int spmv_ring = 1;    // PCG SpMV streams the matrix through shared memory with the TMA (spmv_ring.cuh); 0: row kernel
-    int fused_vec = 1;    // update + direction of a PCG iteration as one kernel with a grid barrier (single GPU)
-    int pdl = 1;          // programmatic dependent launch between the three kernels of a PCG iteration (single GPU)
+    double floor_rtol = 1e-8;   // largest true relative residual mofem_solve accepts as "fp64 floor reached" (converged = 2)
+    int pdl = 1;          // programmatic dependent launch between the two kernels of a PCG iteration (single GPU, peer transport)
     int cell_kernel = 0;  // 1: quad4 overlay cells on the warp-cooperative cell kernel (bit-identical, measured slower: 3.1 vs 2.55 ms at syn-1M)
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -440,7 +440,7 @@ static DevSystem system_of(mofem_ctx *ctx)
     A.n_blk = ctx->C.n_upair;   // upper bound of the sub-blocks in the owned rows (exact on a single GPU)
     return A;
 }
-static const DistPlan *dist_of(mofem_ctx *ctx) { return ctx->have_halo ? &ctx->dist : nullptr; }
+static DistPlan *dist_of(mofem_ctx *ctx) { return ctx->have_halo ? &ctx->dist : nullptr; }
 
 int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, const double *fixed_value)
 {
@@ -470,9 +470,9 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
         W.p = slab; W.r = slab + npad; W.dinv = slab + 2 * npad; W.q = slab + 3 * npad; W.x = slab + 4 * npad;
         W.b = slab + 5 * npad; W.ufix = slab + 6 * npad;
         ctx->slab = slab; ctx->slab_vec_bytes = sizeof(double) * (size_t)npad; ctx->slab_hot_bytes = 5 * ctx->slab_vec_bytes;
-        if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
-            (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
-            (rc = dev_alloc(ctx, &W.sc, 16, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+        for (int j = 0; j < 5; j++)
+            if ((rc = dev_alloc(ctx, &W.part[j], PCG_MAX_PART, pool))) return rc;
+        if ((rc = dev_alloc(ctx, &W.sc, SC_COUNT, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;
@@ -535,7 +535,7 @@ int mofem_solve(mofem_ctx *ctx, double rtol, int32_t maxit, double *u, mofem_sol
             cudaGetLastError();
         }
     }
-    ctx->W.use_ring = ctx->spmv_ring; ctx->W.use_pdl = ctx->pdl; ctx->W.use_fused = ctx->fused_vec;
+    ctx->W.use_ring = ctx->spmv_ring; ctx->W.use_pdl = ctx->pdl; ctx->W.floor_rtol = ctx->floor_rtol;
     cudaError_t run_err = pcg_run(system_of(ctx), ctx->fixed, ctx->W, dist_of(ctx), rtol, maxit, PCG_CHUNK, info, s,
                                   &ctx->launches[3], prof, ctx->prof_ms, ctx->profile);
     if (window) {
@@ -565,9 +565,9 @@ int mofem_energy(mofem_ctx *ctx, double *energy)
     if (!ctx || !ctx->have_solution || !energy) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_energy: call mofem_solve first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    CK(energy_of(system_of(ctx), ctx->u, ctx->W, dist_of(ctx), ctx->W.sc + 6, s));
+    CK(energy_of(system_of(ctx), ctx->u, ctx->W, dist_of(ctx), ctx->W.sc + SC_ENERGY, s));
     double e = 0;
-    CK(cudaMemcpyAsync(&e, ctx->W.sc + 6, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&e, ctx->W.sc + SC_ENERGY, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *energy = 0.5 * e;
     return MOFEM_OK;
@@ -695,6 +695,8 @@ int mofem_p2p_export(mofem_ctx *ctx, uint8_t handle[64], int64_t *n_ghost)
     CK(cudaSetDevice(ctx->device));
     p2p_close(ctx);
     DistPlan &D = ctx->dist;
+    if (D.world > P2P_MAX_WORLD)   // one thread and one shared staging slot per rank in the mailbox code
+        return ctx_fail(ctx, MOFEM_E_LIMIT, "mofem_p2p_export: peer transport supports at most " + std::to_string(P2P_MAX_WORLD) + " ranks (use the NCCL transport)");
     D.n_ghost = D.recv_ptr.back();
     const size_t bytes = sizeof(double) * (size_t)p2p_buffer_doubles(D.world, D.n_owned_node + D.n_ghost);
     CK(cudaMalloc(&D.xbuf, bytes));        // plain cudaMalloc: pool memory cannot be exported through legacy IPC handles
@@ -950,7 +952,7 @@ int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "l2_persist")) { ctx->l2_persist = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "l2_window")) { ctx->l2_window = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "spmv_ring")) { ctx->spmv_ring = (int)value; return MOFEM_OK; }
-    if (!strcmp(name, "fused_vec")) { ctx->fused_vec = (int)value; return MOFEM_OK; }
+    if (!strcmp(name, "floor_rtol_1e12")) { ctx->floor_rtol = (double)value * 1e-12; return MOFEM_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = (int)value; return MOFEM_OK; }
     if (!strcmp(name, "cell_kernel")) { ctx->cell_kernel = (int)value; return MOFEM_OK; }   // takes effect at the next mofem_symbolic
     return ctx_fail(ctx, MOFEM_E_ARG, std::string("mofem_set_option: unknown option ") + name);

@@ -249,11 +249,12 @@ class Context:
         return self
 
     def pcg_profile(self) -> dict:
-        """Summed device time (ms) of the three PCG kernels over the last solve (needs ``set_profile(True)``)."""
+        """Summed device time (ms) of the two PCG kernels (SpMV incl. exchange / vector kernel) over the sampled iterations of
+        the last solve (needs ``set_profile(N)``)."""
         ms = (C.c_double * 3)()
         it = C.c_int64(0)
         self._ck(self._L.mofem_get_pcg_profile(self._h, ms, C.byref(it)))
-        return dict(spmv_ms=ms[0], update_ms=ms[1], direction_ms=ms[2], iterations=int(it.value))
+        return dict(spmv_ms=ms[0], vec_ms=ms[1], iterations=int(it.value))
 
     def timing(self) -> dict:
         ms = (C.c_double * 6)()

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import math
 import time
+import warnings
 
 import numpy as np
 
@@ -397,8 +398,13 @@ def _run(input_data, solver, overlapping_mesh=None, polygons=None, node_elements
     ctx.set_system(f.reshape(-1), fixed, value)
     print("Imposing constraints costs %s seconds." % (time.time() - t))
     t = time.time()
+    # raises RuntimeError (MOFEM_E_NOCONV) unless the TRUE residual is <= RTOL, or stagnated at the fp64 floor of this
+    # matrix below the library's bound (1e-8): the reference's direct solve has no such failure mode, so it is never silent
     u, info = ctx.solve(rtol=RTOL, maxit=MAXIT)
     last_solve_info = info
+    if info["converged"] == 2:
+        warnings.warn("PCG stopped at the fp64 floor of this system: true relative residual %.2e (requested %.0e)"
+                      % (info["relres_true"], RTOL), RuntimeWarning, stacklevel=3)
     if report:      # AMORE.py:685-687 / 1108-1110
         indptr, indices, data = ctx.csr()
         free = fixed == 0

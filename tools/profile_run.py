@@ -36,12 +36,12 @@ if configs:      # e.g. configs=ring:pdl,ring,pdl,none   (each: the switches tha
         on = set(c.split(":"))
         win = [int(t[1:]) for t in on if t[:1] == "w" and t[1:].isdigit()]
         runs.append(dict(spmv_ring=int("ring" in on), pdl=int("pdl" in on), l2_persist=int("l2" in on), profile=int("prof" in on),
-                         l2_window=win[0] if win else 5, fused_vec=int("fused" in on)))
+                         l2_window=win[0] if win else 5))
 else:
     runs.append(dict(spmv_ring=int(kv.get("spmv_ring", 1)), pdl=int(kv.get("pdl", 1)), l2_persist=int(kv.get("l2_persist", 0)),
-                     profile=int(kv.get("profile", 0)), l2_window=int(kv.get("l2_window", 5)), fused_vec=int(kv.get("fused_vec", 1))))
+                     profile=int(kv.get("profile", 0)), l2_window=int(kv.get("l2_window", 5))))
 for opt in runs:
-    for k in ("spmv_ring", "pdl", "l2_persist", "l2_window", "fused_vec"):
+    for k in ("spmv_ring", "pdl", "l2_persist", "l2_window"):
         ctx.set_option(k, opt[k])
     ctx.set_profile(bool(opt["profile"]))
     best = None
