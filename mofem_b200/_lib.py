@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmofem_b200.so")
+# MOFEM_B200_LIB: another build of the same library (kernel experiments); the default is the in-tree one
+LIB_PATH = os.environ.get("MOFEM_B200_LIB") or os.path.join(_HERE, "libmofem_b200.so")
 
 c_d_p = C.POINTER(C.c_double)
 c_i32_p = C.POINTER(C.c_int32)

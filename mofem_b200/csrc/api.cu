@@ -470,9 +470,9 @@ int mofem_set_system(mofem_ctx *ctx, const double *rhs, const uint8_t *fixed, co
         W.p = slab; W.r = slab + npad; W.dinv = slab + 2 * npad; W.q = slab + 3 * npad; W.x = slab + 4 * npad;
         W.b = slab + 5 * npad; W.ufix = slab + 6 * npad;
         ctx->slab = slab; ctx->slab_vec_bytes = sizeof(double) * (size_t)npad; ctx->slab_hot_bytes = 5 * ctx->slab_vec_bytes;
-        for (int j = 0; j < 5; j++)
-            if ((rc = dev_alloc(ctx, &W.part[j], PCG_MAX_PART, pool))) return rc;
-        if ((rc = dev_alloc(ctx, &W.sc, SC_COUNT, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
+        if ((rc = dev_alloc(ctx, &W.part_a, PCG_MAX_PART, pool)) ||
+            (rc = dev_alloc(ctx, &W.part_b, PCG_MAX_PART, pool)) || (rc = dev_alloc(ctx, &W.part_c, PCG_MAX_PART, pool)) ||
+            (rc = dev_alloc(ctx, &W.sc, 16, pool)) || (rc = dev_alloc(ctx, &W.counters, 8, pool)) || (rc = dev_alloc(ctx, &W.row_halo, n / 2 + 1, pool)) || (rc = dev_alloc(ctx, &ctx->fixed, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->rhs, n, pool)) || (rc = dev_alloc(ctx, &ctx->fixed_val, n, pool)) ||
             (rc = dev_alloc(ctx, &ctx->u, n, pool)))
             return rc;
@@ -565,9 +565,9 @@ int mofem_energy(mofem_ctx *ctx, double *energy)
     if (!ctx || !ctx->have_solution || !energy) return ctx_fail(ctx, MOFEM_E_ARG, "mofem_energy: call mofem_solve first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    CK(energy_of(system_of(ctx), ctx->u, ctx->W, dist_of(ctx), ctx->W.sc + SC_ENERGY, s));
+    CK(energy_of(system_of(ctx), ctx->u, ctx->W, dist_of(ctx), ctx->W.sc + 6, s));
     double e = 0;
-    CK(cudaMemcpyAsync(&e, ctx->W.sc + SC_ENERGY, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&e, ctx->W.sc + 6, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *energy = 0.5 * e;
     return MOFEM_OK;

@@ -149,14 +149,13 @@ struct DistPlan {
     int64_t n_halo_rows = 0, halo_rows_cap = 0;
 };
 
+constexpr int P2P_MAX_WORLD = 64;              // one thread per rank in the mailbox code, shared staging of that size
 // Exchange-buffer layout (doubles), identical on every rank (world = W <= P2P_MAX_WORLD):
-//   mailbox  [parity 0..1][src rank][P2P_MBOX_WORDS x u64] = {stamp32 | 32 payload bits}: 5 doubles per iteration   24 W words
-//   hflag    [parity 0..1][src rank]                                                                                  2 W doubles
+//   mailbox  [site 0..1][parity 0..1][src rank][4 x u64] = {stamp32 | 32 payload bits} x 4 (two doubles)   16 W words
+//   hflag    [parity 0..1][src rank]                                          2 W doubles
 //   slab     p, r, dinv, q, x, b, ufix -- the PCG vectors live HERE on the peer path (p first: [owned | ghost nodes][2]),
 //            so that neighbours write their boundary entries straight into the ghost segment of p and the SpMV gathers
-//            from one contiguous vector; starts on a 128-byte line
-constexpr int P2P_MAX_WORLD = 64;              // one thread per rank in the mailbox code, shared staging of that size
-constexpr int P2P_MBOX_WORDS = 12;             // 5 doubles = 10 words, padded
+//            from one contiguous vector
 struct P2PDev {
     double *const *peer;   // device array [world]
     double *local;         // == peer[rank]
@@ -166,34 +165,23 @@ struct P2PDev {
     int *err;              // set to 1 when a wait times out
     unsigned int stamp32;  // 32-bit stamp carried inside every mailbox word
 };
-__host__ __device__ inline int64_t p2p_mbox_off(int W, int parity, int src) { return ((int64_t)parity * W + src) * P2P_MBOX_WORDS; }
-__host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 2 * (int64_t)P2P_MBOX_WORDS * W + (int64_t)parity * W + src; }
-__host__ __device__ inline int64_t p2p_p_off(int W) { return ((2 * (int64_t)P2P_MBOX_WORDS + 2) * W + 15) & ~(int64_t)15; }
+__host__ __device__ inline int64_t p2p_mbox_off(int W, int site, int parity, int src) { return ((int64_t)(site * 2 + parity) * W + src) * 4; }
+__host__ __device__ inline int64_t p2p_hflag_off(int W, int parity, int src) { return 16 * (int64_t)W + (int64_t)parity * W + src; }
+__host__ __device__ inline int64_t p2p_p_off(int W) { return (18 * (int64_t)W + 15) & ~(int64_t)15; }   // the slab starts on a 128-byte line
 inline int64_t p2p_slab_pad(int64_t n_local_dof) { return (n_local_dof + 31) & ~(int64_t)31; }
-// mailboxes + flags + the whole PCG vector slab (p first): one allocation
+// mailboxes + flags + the whole PCG vector slab (p first): one allocation, one L2 persistence window
 inline int64_t p2p_buffer_doubles(int W, int64_t n_local_node) { return p2p_p_off(W) + 7 * p2p_slab_pad(2 * n_local_node) + 8; }
 
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed /*or null*/, cudaStream_t s);
 
-// Scalars of the PCG loop (PcgBuffers::sc).  One all-reduce per iteration carries the five sums [SC_PQ .. SC_RR].
-enum {
-    SC_PQ = 0, SC_QZ = 1, SC_QDQ = 2, SC_RZ = 3, SC_RR = 4,   // reduced over all ranks: what the vector kernel consumes
-    SC_LOC_RZ = 5, SC_LOC_RR = 6,                             // this rank's r.z and r.r of the CURRENT residual
-    SC_PART = 8,                                              // [8..12] NCCL transport: this rank's five partial sums
-    SC_BNORM2 = 13, SC_RR_TRUE = 14, SC_ENERGY = 15,
-    SC_DONE = 16,                                             // raised by the vector kernel that sees r.r <= tol^2
-    SC_IT_DONE = 17,                                          // ... the number of updates x has received at that point
-    SC_COUNT = 24
-};
-
 constexpr int PCG_MAX_PART = 4096;
 struct PcgBuffers {
     double *x, *r, *p, *q, *dinv, *b, *ufix;  // n each
-    double *part[5];                           // PCG_MAX_PART each: per-CTA partial sums
-    double *sc;                                // SC_COUNT scalars
+    double *part_a, *part_b, *part_c;          // PCG_MAX_PART each
+    double *sc;                                // 16 scalars (pcg.cu: SC_*)
     uint8_t *row_halo;                         // [local nodes] 1 = row references a ghost column (peer path)
-    unsigned int *counters;                    // 8 words: [0] SpMV, [1] vector kernel / init, [2] true residual, [3] energy: arrival counters of
-                                               // the grid-wide reductions; [5] stop-flag arrivals; [6] peer time-out flag; [7] largest node-row degree
+    unsigned int *counters;                    // 8 words: arrival counters of the grid-wide reductions, [6] = time-out flag (peer wait / grid barrier),
+                                               // [4] = arrivals of the vector kernel, [7] = largest node-row degree (written by pcg_setup)
     // TMA-ring SpMV (spmv_ring.cuh): tile table built by pcg_setup; capacity in tiles
     void *ring_tiles = nullptr;
     int64_t ring_cap = 0;

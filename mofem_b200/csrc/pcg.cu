@@ -5,33 +5,27 @@
 // search directions are zero on fixed DOFs and the SpMV zeroes fixed rows, so the iteration is exactly CG on the
 // reduced free-free system without building a second matrix.
 //
-// One iteration = TWO kernels and ONE reduction point (on any number of GPUs):
-//   SpMV     q = K p, and for the rows it produces the three sums  p.q,  q.z,  q.D^-1.q   (z = D^-1 r).  Its last CTA adds
-//            the two sums  r.z, r.r  of the CURRENT residual (left behind by the previous vector kernel) and hands the five
-//            numbers on: into sc[] on one GPU, into every peer's mailbox over NVLink (peer transport), or to one
-//            ncclAllReduce (NCCL transport).
-//   vector   alpha = r.z / p.q;  the r.z of the NEXT residual follows from the sums without touching the vectors,
-//            r'.z' = r.z - 2 alpha q.z + alpha^2 q.D^-1.q, so beta = r'.z' / r.z is known up front and one pass does
-//            x += alpha p,  r -= alpha q,  p = D^-1 r + beta p  and the direct sums r.z, r.r of the new residual.
-// The predicted r'.z' is used for beta only; alpha and the convergence test always use directly summed values, so the
-// recurrence cannot drift.  The classical form needs a second reduction between the residual update and the direction
-// update (two grid-wide / machine-wide sync points per iteration); this form has one.
-//
 // The matrix is the scalar CSR viewed at node level (one column index per 2x2 sub-block: 9 bytes per stored scalar
 // instead of 12).  Two SpMV kernels read it:
 //   k_spmv_ring (spmv_ring.cuh)  the SpMV of the PCG loop: a producer warp streams row tiles into a shared-memory ring with
-//                                cp.async.bulk (TMA), consumer warps multiply out of shared memory; <true> variant with the
+//                                cp.async.bulk (TMA), consumer warps multiply out of shared memory; _p2p variant with the
 //                                NVLink halo exchange inside the kernel
 //   k_spmv                       row kernel (8 lanes per node row chase pointer -> {index, values} -> x through global
 //                                loads, 4 independent load groups per lane, evict-first streaming): mofem_spmv, residual
 //                                checks, energy, the NCCL transport, rows too long for a ring stage
-// The kernels of the loop are chained with programmatic dependent launch (single GPU and peer transport): the ring's
-// producer fills its stages while the vector kernel drains.
+// The vector part of an iteration is ONE kernel, k_pcg_vec:
+//     r -= alpha q, sums of r.z and r.r  |  arrive  |  x += alpha p  |  wait  |  p = z + beta p
+// The second reduction of the iteration (beta needs r.z of the NEW residual) is the arrive/wait pair -- a grid barrier on one
+// GPU, the peers' mailboxes on the peer transport -- and the x update, which needs neither sum, sits between the two so that
+// the barrier / NVLink latency is spent working.  (A single-reduction PCG, which gets beta from q.z and q.D^-1.q summed
+// inside the SpMV, was built and measured: the extra sums cost the SpMV more than the hidden second reduction costs here;
+// DESIGN.md has the numbers.)  The kernels are chained with programmatic dependent launch on one GPU and on the peer
+// transport: the ring's producer fills its stages while the vector kernel drains.
 //
 // Dot products have a fixed reduction order (bit-reproducible): per-thread sums over a static assignment, per-CTA
-// partials summed in index order by the last CTA to finish, per-rank sums added in rank order.  alpha/beta live on the
-// device; the vector kernel that sees r.r <= tol^2 raises a stop flag which turns the rest of the enqueued chunk into
-// no-ops, so the host polls only every PCG_CHUNK iterations.
+// partials summed in index order, per-rank sums added in rank order.  alpha/beta live on the device; the vector kernel
+// that sees r.r <= tol^2 raises a stop flag which turns the rest of the enqueued chunk into no-ops, so the host polls only
+// every PCG_CHUNK iterations.
 #include <algorithm>
 
 #include "common.cuh"
@@ -43,11 +37,19 @@ constexpr int VEC_BLOCK = 256;
 constexpr int SPMV_BLOCK = 128;
 constexpr int SPMV_LANES = 8;    // lanes cooperating on one node row
 constexpr int SPMV_UNROLL = 4;   // independent load groups per lane
-constexpr int SPMV_MINB = 12;    // resident blocks per SM
+constexpr int SPMV_MINB = 12;    // resident blocks per SM (42 registers per thread)
 constexpr int SPMV_GRID_CAP = 148 * 24;
 static_assert(SPMV_GRID_CAP <= PCG_MAX_PART, "partials buffer too small");
 
-struct Parts { double *p[5]; };   // per-CTA partial sums: [0..2] SpMV (p.q, q.z, q.D^-1.q), [3..4] vector kernel (r.z, r.r)
+// scalar slots in PcgBuffers::sc: (rz, rr) pairs double-buffered by iteration parity at [0,1] and [2,3] -- each pair
+// is contiguous so that the row-partitioned solve all-reduces it in one call.
+enum { SC_BNORM2 = 4, SC_RR_TRUE = 5, SC_ENERGY = 6, SC_PQ = 7, SC_DONE = 8, SC_IT_DONE = 9, SC_PART_RZ = 10, SC_PART_PQ = 12, SC_COUNT = 16 };
+// SC_PART_*: per-rank partials on the NCCL path (all-reduced INTO the global slots, so that re-reducing after the device
+// has stopped is idempotent).
+// SC_DONE: set by the direction kernel of the iteration whose recurrence residual met the tolerance; every later kernel
+// of the chunk returns at once, so the host can poll rarely (large chunks) without paying for overshoot iterations.
+__host__ __device__ inline int sc_rz(int it) { return 2 * (it & 1); }
+__host__ __device__ inline int sc_rr(int it) { return 2 * (it & 1) + 1; }
 
 // block-wide sum, result valid in every thread; fixed order
 __device__ __forceinline__ double block_sum(double v, double *sm)
@@ -64,51 +66,34 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
     return s;
 }
 
-// Publishes this block's N partials under one counter; the last block to arrive returns true after which total[] (valid
-// in every thread of that block) holds the sums of all partials in index order -- independent of which block came last.
-template <int N>
-__device__ __forceinline__ bool grid_sum_n(const double (&v)[N], double *const *part, unsigned int *counter, double *sm,
-                                           double (&total)[N])
+// Publishes this block's partial; the last block to arrive returns true after which `total` (valid in every
+// thread of that block) is the sum of all partials in index order -- independent of which block came last.
+__device__ __forceinline__ bool grid_sum(double partial, double *__restrict__ part, unsigned int *counter, double *sm,
+                                         double &total)
 {
     __shared__ bool is_last;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < N; j++) part[j][blockIdx.x] = v[j];
+        part[blockIdx.x] = partial;
         __threadfence();
-        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    double a[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) a[j] = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-#pragma unroll
-        for (int j = 0; j < N; j++) a[j] += __ldcg(part[j] + i);
-    }
-#pragma unroll
-    for (int j = 0; j < N; j++) total[j] = block_sum(a[j], sm);
+    double v = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(part + i);
+    total = block_sum(v, sm);
     if (threadIdx.x == 0) *counter = 0u;
     return true;
 }
 
-__device__ __forceinline__ bool grid_sum(double partial, double *part, unsigned int *counter, double *sm, double &total)
-{
-    const double v[1] = {partial};
-    double *const pp[1] = {part};
-    double t[1];
-    const bool last = grid_sum_n<1>(v, pp, counter, sm, t);
-    total = t[0];
-    return last;
-}
-
 // ---- NVLink peer-memory primitives (row-partitioned solve, one process per GPU) ---------------------------------
-// Every rank owns an exchange buffer that all peers map (CUDA IPC).  Halo values travel as {payload, stamp}: the writer
+// Every rank owns an exchange buffer that all peers map (CUDA IPC).  A value travels as {payload, stamp}: the writer
 // stores the payload into the consumer's buffer, fences at system scope, then stores the stamp; the consumer polls the
 // stamp in its OWN memory.  Stamps grow monotonically (epoch, iteration), two parity slots make reuse safe: a rank can
 // only be two rounds ahead of a peer after that peer has consumed the older round.
-constexpr long long P2P_TIMEOUT_CLOCKS = 40000000000ll;   // ~20 s at 2 GHz: a peer died
+constexpr long long P2P_TIMEOUT_CLOCKS = 40000000000ll;   // ~20 s at 2 GHz: a peer died (or a CTA never became resident)
 __device__ __forceinline__ bool p2p_wait(const volatile double *flag, double stamp, int *err)
 {
     long long t0 = 0;
@@ -122,38 +107,37 @@ __device__ __forceinline__ bool p2p_wait(const volatile double *flag, double sta
     return true;
 }
 
-// All-reduce of the five sums of an iteration in "LL" form (the trick NCCL's low-latency protocol uses): every 8-byte word
-// carries 32 bits of payload and a 32-bit stamp, and an aligned 8-byte store is atomic over NVLink -- so no fence and no
+// All-reduce of one or two doubles in "LL" form (the trick NCCL's low-latency protocol uses): every 8-byte word carries
+// 32 bits of payload and a 32-bit stamp, and an aligned 8-byte store is atomic over NVLink -- so no fence and no
 // separate flag: one-way latency only.
-// producer side: called by ONE block (>= world threads) after it holds this rank's five sums
-__device__ __forceinline__ void p2p_publish5(const P2PDev &pp, const double (&v)[5])
+__device__ __forceinline__ unsigned int p2p_stamp32(const P2PDev &pp) { return pp.stamp32; }
+
+// producer side: called by ONE block after it holds this rank's partial(s)
+__device__ __forceinline__ void p2p_publish(const P2PDev &pp, int site, double v0, double v1)
 {
     if ((int)threadIdx.x < pp.world) {
         volatile unsigned long long *slot =
-            reinterpret_cast<volatile unsigned long long *>(pp.peer[threadIdx.x] + p2p_mbox_off(pp.world, pp.parity, pp.rank));
+            reinterpret_cast<volatile unsigned long long *>(pp.peer[threadIdx.x] + p2p_mbox_off(pp.world, site, pp.parity, pp.rank));
         const unsigned long long f = (unsigned long long)pp.stamp32 << 32;
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            const unsigned long long a = (unsigned long long)__double_as_longlong(v[j]);
-            slot[2 * j] = f | (a & 0xffffffffull);
-            slot[2 * j + 1] = f | (a >> 32);
-        }
+        const unsigned long long a = (unsigned long long)__double_as_longlong(v0), c = (unsigned long long)__double_as_longlong(v1);
+        slot[0] = f | (a & 0xffffffffull); slot[1] = f | (a >> 32);
+        slot[2] = f | (c & 0xffffffffull); slot[3] = f | (c >> 32);
     }
 }
 
-// consumer side: every block (>= world threads) sums the W contributions in rank order (bit-identical on every rank and block)
-__device__ __forceinline__ void p2p_collect5(const P2PDev &pp, double (&v)[5])
+// consumer side: every block sums the W partials in rank order (bit-identical on every rank and block)
+__device__ __forceinline__ void p2p_collect(const P2PDev &pp, int site, double &v0, double &v1)
 {
-    __shared__ double sv[5][P2P_MAX_WORLD];
+    __shared__ double sv[2][P2P_MAX_WORLD];
     if ((int)threadIdx.x < pp.world) {
         const volatile unsigned long long *slot =
-            reinterpret_cast<const volatile unsigned long long *>(pp.local + p2p_mbox_off(pp.world, pp.parity, threadIdx.x));
-        unsigned long long wv[10];
+            reinterpret_cast<const volatile unsigned long long *>(pp.local + p2p_mbox_off(pp.world, site, pp.parity, threadIdx.x));
+        unsigned long long wv[4];
         long long t0 = 0;
         for (unsigned spins = 0;; spins++) {
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < 10; j++) { wv[j] = slot[j]; ok = ok && (unsigned int)(wv[j] >> 32) == pp.stamp32; }
+            for (int j = 0; j < 4; j++) { wv[j] = slot[j]; ok = ok && (unsigned int)(wv[j] >> 32) == pp.stamp32; }
             if (ok) break;
             if ((spins & 0xfff) == 0xfff) {
                 const long long now = clock64();
@@ -161,17 +145,13 @@ __device__ __forceinline__ void p2p_collect5(const P2PDev &pp, double (&v)[5])
                 else if (now - t0 > P2P_TIMEOUT_CLOCKS) { *pp.err = 1; break; }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 5; j++)
-            sv[j][threadIdx.x] = __longlong_as_double((long long)((wv[2 * j] & 0xffffffffull) | (wv[2 * j + 1] << 32)));
+        sv[0][threadIdx.x] = __longlong_as_double((long long)((wv[0] & 0xffffffffull) | (wv[1] << 32)));
+        sv[1][threadIdx.x] = __longlong_as_double((long long)((wv[2] & 0xffffffffull) | (wv[3] << 32)));
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        double a = 0.0;
-        for (int r = 0; r < pp.world; r++) a += sv[j][r];
-        v[j] = a;
-    }
+    double a = 0.0, c = 0.0;
+    for (int r = 0; r < pp.world; r++) { a += sv[0][r]; c += sv[1][r]; }
+    v0 = a; v1 = c;
     __syncthreads();
 }
 
@@ -187,12 +167,6 @@ struct HaloPush {          // peer path: what a kernel needs to deliver this ran
 // read x through the non-coherent path (ld.global.nc is only defined for data that stays constant for the kernel's
 // lifetime, and an interior row may already have pulled the sector shared by the last owned and the first ghost node into
 // L1): COHERENT loads x with ld.global.cg (L2, the point the NVLink stores land in).
-template <bool COHERENT>
-__device__ __forceinline__ double2 load_x(const double2 *p)
-{
-    return COHERENT ? __ldcg(p) : __ldg(p);
-}
-
 // one node row (two scalar rows) by a group of SPMV_LANES lanes; the sums are valid in every lane of the group
 template <bool COHERENT = false>
 __device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__restrict__ node_ptr,
@@ -212,7 +186,8 @@ __device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__re
                 const int c = __ldg(node_idx + r0 + kk);
                 v0[u] = __ldcs(d0 + kk);
                 v1[u] = __ldcs(d1 + kk);
-                xv[u] = load_x<COHERENT>(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
+                xv[u] = COHERENT ? __ldcg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c))
+                                 : __ldg(reinterpret_cast<const double2 *>(x + 2 * (int64_t)c));
             } else {
                 v0[u] = v1[u] = xv[u] = make_double2(0.0, 0.0);
             }
@@ -225,98 +200,65 @@ __device__ __forceinline__ void spmv_row(int64_t a, int sub, const int64_t *__re
     }
 }
 
-// reduces the lanes of a row group, masks fixed rows, stores y and adds the row to the sums (lane sub == 0)
-template <int MODE>
-__device__ __forceinline__ void spmv_finish_row(int64_t a, int sub, double y0, double y1, double *__restrict__ y,
-                                                const uint8_t *__restrict__ fixed, const double *x, const double *r,
-                                                const double *dinv, RingDots &dots)
-{
-#pragma unroll
-    for (int d = SPMV_LANES / 2; d; d >>= 1) {
-        y0 += __shfl_xor_sync(0xffffffffu, y0, d);
-        y1 += __shfl_xor_sync(0xffffffffu, y1, d);
-    }
-    if (a >= 0 && sub == 0) {
-        if (fixed) {
-            const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
-            if (fx.x) y0 = 0.0;
-            if (fx.y) y1 = 0.0;
-        }
-        *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
-        if (MODE == 1) {
-            const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
-            dots.pq = fma(xa.x, y0, dots.pq); dots.pq = fma(xa.y, y1, dots.pq);
-        }
-        if (MODE == 2)
-            ring_row_dots(dots, *reinterpret_cast<const double2 *>(x + 2 * a), *reinterpret_cast<const double2 *>(r + 2 * a),
-                          *reinterpret_cast<const double2 *>(dinv + 2 * a), y0, y1);
-    }
-}
-
-// End of a PCG SpMV: the CTA's three sums -> grid totals; the last CTA appends r.z and r.r of the current residual and hands
-// the five numbers on (out5: sc + SC_PQ on one GPU, sc + SC_PART for the NCCL all-reduce; peer transport: the mailboxes).
-template <bool P2P>
-__device__ __forceinline__ void pcg_spmv_epilogue(const RingDots &dots, Parts part, unsigned int *counter, double *sc,
-                                                  double *out5, const P2PDev &pp, double *sm)
-{
-    const double v[3] = {block_sum(dots.pq, sm), block_sum(dots.qz, sm), block_sum(dots.qdq, sm)};
-    double t[3];
-    if (grid_sum_n<3>(v, part.p, counter, sm, t)) {
-        const double five[5] = {t[0], t[1], t[2], __ldcg(sc + SC_LOC_RZ), __ldcg(sc + SC_LOC_RR)};
-        if (P2P) p2p_publish5(pp, five);
-        else if (threadIdx.x == 0) {
-#pragma unroll
-            for (int j = 0; j < 5; j++) out5[j] = five[j];
-        }
-    }
-}
-
-// this rank's boundary entries of x -> the ghost segments of the neighbours' x over NVLink, then the stamp; called by the
-// `nthr` threads of ONE CTA that share `sync`
-template <class Sync>
-__device__ __forceinline__ void push_halo(const HaloPush &hp, const P2PDev &pp, const double *x, int nthr, Sync sync)
-{
-    const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    for (int64_t i = threadIdx.x; i < hp.n_send; i += nthr) {
-        const int k = hp.send_nb[i];
-        double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
-        *dst = x2[hp.send_idx[i]];
-    }
-    __threadfence_system();
-    sync();
-    if ((int)threadIdx.x < hp.n_nb)
-        *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
-}
-
-// y = K x on node rows; fixed rows -> 0.  Ghost columns are the tail of x.
-// MODE 0: product only.  MODE 1: also x.y -> *out (energy).  MODE 2: SpMV of the PCG loop (sums and hand-off as above).
+// y = K x on node rows; fixed rows -> 0.  Optionally the dot product x.y goes to *dot_out.  Ghost columns are the tail
+// of x.
 // P2P (row-partitioned, peer transport) -- one kernel does the halo exchange, the product and the all-reduce hand-off:
 //   * block 0 first writes this rank's boundary entries of x into the ghost segment of the neighbours' x over NVLink and
 //     raises its stamp there;
 //   * every block first multiplies its rows that touch no ghost column; the few that do (halo_rows) are dealt out afterwards,
 //     behind a wait for the neighbours' stamps -- the NVLink latency hides behind the interior rows;
-//   * the last block publishes the five sums into every peer's mailbox.
-template <int MODE, bool P2P>
+//   * the last block publishes the dot-product partial into every peer's mailbox.
+template <bool DOT, bool P2P>
 __global__ void __launch_bounds__(SPMV_BLOCK, SPMV_MINB)
 k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
        const double *__restrict__ data, const double *x, double *__restrict__ y,
-       const uint8_t *__restrict__ fixed, const double *__restrict__ r, const double *__restrict__ dinv, Parts part,
-       unsigned int *counter, double *sc, double *out, P2PDev pp, int n_wait, const int *__restrict__ wait_rank,
-       const uint8_t *__restrict__ row_halo, const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp)
+       const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter, double *dot_out,
+       P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo,
+       const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp, const double *done_flag)
 {
     __shared__ double sm[SPMV_BLOCK / 32];
     ring::grid_dep_wait();   // PDL: no-op unless launched with the programmatic-serialization attribute
-    if (MODE == 2 && __ldcg(sc + SC_DONE) != 0.0) return;
-    if (P2P && blockIdx.x == 0 && hp.n_nb) push_halo(hp, pp, x, SPMV_BLOCK, [] { __syncthreads(); });
+    if (DOT && done_flag && __ldcg(done_flag) != 0.0) return;
+    if (P2P && blockIdx.x == 0 && hp.n_nb) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        for (int64_t i = threadIdx.x; i < hp.n_send; i += blockDim.x) {
+            const int k = hp.send_nb[i];
+            double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
+            *dst = x2[hp.send_idx[i]];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < hp.n_nb)
+            *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
+    }
     const int sub = threadIdx.x % SPMV_LANES;
     constexpr int64_t rows_per_block = SPMV_BLOCK / SPMV_LANES;
-    RingDots dots{0.0, 0.0, 0.0};
+    double dot = 0.0;
+    auto finish_row = [&](int64_t a, double y0, double y1) {
+#pragma unroll
+        for (int d = SPMV_LANES / 2; d; d >>= 1) {
+            y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+            y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+        }
+        if (a >= 0 && sub == 0) {
+            if (fixed) {
+                const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
+                if (fx.x) y0 = 0.0;
+                if (fx.y) y1 = 0.0;
+            }
+            *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+            if (DOT) {
+                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
+            }
+        }
+    };
     for (int64_t row0 = (int64_t)blockIdx.x * rows_per_block; row0 < n_node; row0 += (int64_t)gridDim.x * rows_per_block) {
         int64_t a = row0 + threadIdx.x / SPMV_LANES;
         if (a >= n_node || (P2P && row_halo[a])) a = -1;        // halo rows come last (below)
         double y0 = 0.0, y1 = 0.0;
         if (a >= 0) spmv_row(a, sub, node_ptr, node_idx, data, x, y0, y1);
-        spmv_finish_row<MODE>(a, sub, y0, y1, y, fixed, x, r, dinv, dots);
+        finish_row(a, y0, y1);
     }
     if (P2P) {
         // rows that gather ghost entries: a compact list, dealt block by block AFTER the interior rows, behind a wait for
@@ -333,20 +275,22 @@ k_spmv(int64_t n_node, const int64_t *__restrict__ node_ptr, const int32_t *__re
                 const int64_t a = i < n_halo ? halo_rows[i] : -1;
                 double y0 = 0.0, y1 = 0.0;
                 if (a >= 0) spmv_row<true>(a, sub, node_ptr, node_idx, data, x, y0, y1);
-                spmv_finish_row<MODE>(a, sub, y0, y1, y, fixed, x, r, dinv, dots);
+                finish_row(a, y0, y1);
             }
         }
     }
-    ring::grid_dep_launch();   // the dependent (vector kernel) may become resident from here on
-    if (MODE == 1) {
-        const double s = block_sum(dots.pq, sm);
+    ring::grid_dep_launch();   // the dependent (update kernel) may become resident from here on
+    if (DOT) {
+        const double s = block_sum(dot, sm);
         double total;
-        if (grid_sum(s, part.p[0], counter, sm, total) && threadIdx.x == 0) *out = total;
+        if (grid_sum(s, part_dot, counter, sm, total)) {
+            if (P2P) p2p_publish(pp, 0, total, 0.0);
+            else if (threadIdx.x == 0) *dot_out = total;
+        }
     }
-    if (MODE == 2) pcg_spmv_epilogue<P2P>(dots, part, counter, sc, out, pp, sm);
 }
 
-// ---- TMA-ring SpMV of the PCG loop (spmv_ring.cuh) -----------------------------------------------------------------
+// ---- TMA-ring SpMV of the single-GPU PCG loop (spmv_ring.cuh) -------------------------------------------------------
 // 2 CTAs per SM, 12 consumer warps + 1 producer warp each, 2 stages of <= 960 rows + sub-blocks (tuned with
 // tools/spmv_lab2.cu inside a PCG-shaped loop: 85 us against 97 us for the row kernel on the 1 M-cell bench matrix).
 using PcgRing = RingCfg<960, 128, 2, 12>;
@@ -377,52 +321,93 @@ __global__ void k_ring_tiles(int64_t n_node, const int64_t *__restrict__ node_pt
         for (int64_t a = a0; a < a1; a++) if (row_mask[a]) { rt.flags = 1; break; }
     tiles[t] = rt;
 }
-// q = K p and the sums of the iteration.  Launched with the PDL attribute the producer warp fills the ring while the vector
-// kernel of the previous iteration is still draining (the matrix does not depend on it).
-// P2P (row-partitioned, peer transport): the same ring for the rows that touch no ghost column, with the halo exchange of
-// k_spmv around it -- CTA 0 first stores this rank's boundary entries of p into the neighbours' ghost segments over NVLink
-// and raises its stamp there; the rows that gather ghosts (a compact list, their tiles carry the mask flag) are multiplied
-// after the ring, behind a wait for the neighbours' stamps; the last CTA publishes the five sums into every peer's mailbox.
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(PcgRing::CW * 32) : "memory"); }
 
-template <bool P2P>
+// q = K p and the CTA's partial of p.q (part_dot[blockIdx.x]: the vector kernel adds the partials up, so this kernel has no
+// "last CTA" tail).  Launched with the PDL attribute the producer warp fills the ring while the vector kernel of the previous
+// iteration is still draining (the matrix does not depend on it).
 __global__ void __launch_bounds__(PcgRing::THREADS, 2)
 k_spmv_ring(int n_tile, const RingTile *__restrict__ tiles, const int64_t *__restrict__ node_ptr,
-            const int32_t *__restrict__ node_idx, const double *__restrict__ data, const double *x, double *__restrict__ y,
-            const uint8_t *__restrict__ fixed, const double *__restrict__ r, const double *__restrict__ dinv, Parts part,
-            unsigned int *counter, double *sc, P2PDev pp, int n_wait, const int *__restrict__ wait_rank,
-            const uint8_t *__restrict__ row_halo, const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp)
+            const int32_t *__restrict__ node_idx, const double *__restrict__ data, const double *__restrict__ x,
+            double *__restrict__ y, const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, const double *done_flag)
 {
     extern __shared__ __align__(128) unsigned char ring_smem[];
     __shared__ double sm[32];
-    const RingState rs = ring_prologue<PcgRing>(ring_smem, n_tile, tiles, node_ptr, node_idx, data, sc + SC_DONE);
-    if (!rs.active) return;
+    double dot = 0.0;
+    if (!ring_spmv_body<PcgRing, true>(ring_smem, n_tile, tiles, node_ptr, node_idx, data, x, y, fixed, dot, nullptr, done_flag)) return;
+    const double s = block_sum(dot, sm);
+    if (threadIdx.x == 0) part_dot[blockIdx.x] = s;
+}
+
+// Row-partitioned, peer transport: the same ring for the rows that touch no ghost column, with the halo exchange of k_spmv
+// around it -- CTA 0 first stores this rank's boundary entries of x into the neighbours' ghost segments over NVLink and raises
+// its stamp there; the rows that gather ghosts (a compact list, their tiles carry the mask flag) are multiplied after the ring,
+// behind a wait for the neighbours' stamps; the last CTA publishes the p.q partial into every peer's mailbox.
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(PcgRing::CW * 32) : "memory"); }
+
+__global__ void __launch_bounds__(PcgRing::THREADS, 2)
+k_spmv_ring_p2p(int n_tile, const RingTile *__restrict__ tiles, int64_t n_node, const int64_t *__restrict__ node_ptr,
+                const int32_t *__restrict__ node_idx, const double *__restrict__ data, const double *x,
+                double *__restrict__ y, const uint8_t *__restrict__ fixed, double *__restrict__ part_dot, unsigned int *counter,
+                P2PDev pp, int n_wait, const int *__restrict__ wait_rank, const uint8_t *__restrict__ row_halo,
+                const int32_t *__restrict__ halo_rows, int64_t n_halo, HaloPush hp, const double *done_flag)
+{
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ double sm[32];
     const bool consumer = (int)(threadIdx.x >> 5) < PcgRing::CW;
     constexpr int NC = PcgRing::CW * 32;
-    if (P2P && blockIdx.x == 0 && hp.n_nb && consumer) push_halo(hp, pp, x, NC, [] { consumer_barrier(); });
-    RingDots dots{0.0, 0.0, 0.0};
-    ring_main<PcgRing, P2P>(ring_smem, rs, n_tile, tiles, node_ptr, node_idx, data, x, y, fixed, r, dinv, dots, row_halo);
-    if (P2P) {
-        constexpr int64_t rows_per_block = NC / SPMV_LANES;
-        const int64_t h0 = (int64_t)blockIdx.x * rows_per_block;
-        if (consumer && h0 < n_halo) {
-            if ((int)threadIdx.x < n_wait)
-                p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
-                         pp.stamp, pp.err);
+    if (blockIdx.x == 0 && hp.n_nb && consumer) {
+        ring::grid_dep_wait();                     // x is the previous kernel's output (the producer warp does not wait here)
+        if (!(done_flag && __ldcg(done_flag) != 0.0)) {
+            const double2 *x2 = reinterpret_cast<const double2 *>(x);
+            for (int64_t i = threadIdx.x; i < hp.n_send; i += NC) {
+                const int k = hp.send_nb[i];
+                double2 *dst = reinterpret_cast<double2 *>(pp.peer[hp.nb_rank[k]] + hp.nb_ghost_off[k]) + hp.send_dst[i];
+                *dst = x2[hp.send_idx[i]];
+            }
+            __threadfence_system();
             consumer_barrier();
-            __threadfence();
-            const int sub = threadIdx.x % SPMV_LANES;
-            for (int64_t i0 = h0; i0 < n_halo; i0 += (int64_t)gridDim.x * rows_per_block) {
-                const int64_t i = i0 + threadIdx.x / SPMV_LANES;
-                const int64_t a = i < n_halo ? halo_rows[i] : -1;
-                double y0 = 0.0, y1 = 0.0;
-                if (a >= 0) spmv_row<true>(a, sub, node_ptr, node_idx, data, x, y0, y1);
-                spmv_finish_row<2>(a, sub, y0, y1, y, fixed, x, r, dinv, dots);
+            if ((int)threadIdx.x < hp.n_nb)
+                *reinterpret_cast<volatile double *>(pp.peer[hp.nb_rank[threadIdx.x]] + p2p_hflag_off(pp.world, pp.parity, pp.rank)) = pp.stamp;
+        }
+    }
+    double dot = 0.0;
+    if (!ring_spmv_body<PcgRing, false, true>(ring_smem, n_tile, tiles, node_ptr, node_idx, data, x, y, fixed, dot, row_halo, done_flag)) return;
+    constexpr int64_t rows_per_block = NC / SPMV_LANES;
+    const int64_t h0 = (int64_t)blockIdx.x * rows_per_block;
+    if (consumer && h0 < n_halo) {
+        if ((int)threadIdx.x < n_wait)
+            p2p_wait(reinterpret_cast<const volatile double *>(pp.local + p2p_hflag_off(pp.world, pp.parity, wait_rank[threadIdx.x])),
+                     pp.stamp, pp.err);
+        consumer_barrier();
+        __threadfence();
+        const int sub = threadIdx.x % SPMV_LANES;
+        for (int64_t i0 = h0; i0 < n_halo; i0 += (int64_t)gridDim.x * rows_per_block) {
+            const int64_t i = i0 + threadIdx.x / SPMV_LANES;
+            const int64_t a = i < n_halo ? halo_rows[i] : -1;
+            double y0 = 0.0, y1 = 0.0;
+            if (a >= 0) spmv_row<true>(a, sub, node_ptr, node_idx, data, x, y0, y1);
+#pragma unroll
+            for (int d = SPMV_LANES / 2; d; d >>= 1) {
+                y0 += __shfl_xor_sync(0xffffffffu, y0, d);
+                y1 += __shfl_xor_sync(0xffffffffu, y1, d);
+            }
+            if (a >= 0 && sub == 0) {
+                if (fixed) {
+                    const uchar2 fx = *reinterpret_cast<const uchar2 *>(fixed + 2 * a);
+                    if (fx.x) y0 = 0.0;
+                    if (fx.y) y1 = 0.0;
+                }
+                *reinterpret_cast<double2 *>(y + 2 * a) = make_double2(y0, y1);
+                const double2 xa = *reinterpret_cast<const double2 *>(x + 2 * a);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
             }
         }
     }
-    ring::grid_dep_launch();   // the vector kernel may become resident from here on
-    pcg_spmv_epilogue<P2P>(dots, part, counter, sc, sc + SC_PQ, pp, sm);
+    (void)n_node;
+    ring::grid_dep_launch();       // the vector kernel may become resident from here on
+    const double s = block_sum(dot, sm);
+    double total;
+    if (grid_sum(s, part_dot, counter, sm, total)) p2p_publish(pp, 0, total, 0.0);
 }
 
 // kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start while its
@@ -481,12 +466,33 @@ __global__ void k_build_rhs(int64_t n, const uint8_t *__restrict__ fixed, const 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) b[i] = fixed[i] ? 0.0 : f[i] - Kufix[i];
 }
+
+// Publishes two partials per block under one counter; the last block sums both lists in index order.
+__device__ __forceinline__ bool grid_sum2(double s1, double s2, double *__restrict__ part1, double *__restrict__ part2,
+                                          unsigned int *counter, double *sm, double &t1, double &t2)
+{
+    __shared__ bool is_last2;
+    if (threadIdx.x == 0) {
+        part1[blockIdx.x] = s1; part2[blockIdx.x] = s2;
+        __threadfence();
+        is_last2 = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last2) return false;
+    __threadfence();
+    double a = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { a += __ldcg(part1 + i); c += __ldcg(part2 + i); }
+    t1 = block_sum(a, sm); t2 = block_sum(c, sm);
+    if (threadIdx.x == 0) *counter = 0u;
+    return true;
+}
+
 // The vector kernels work on double2 (n = 2 * n_node is even).
-// init: x = 0, r = b (or keep x, r), p = dinv*r ; this rank's r.z and r.r -> sc[SC_LOC_*] (the first SpMV hands them on);
-// a fresh solve also leaves r.r = |b|^2 (this rank's part) in sc[SC_BNORM2]
+// init: x = 0, r = b (or keep x, r), p = dinv*r ; rz = r.dinv.r, rr = r.r
 __global__ void __launch_bounds__(VEC_BLOCK)
 k_pcg_init(int64_t n2, const double2 *__restrict__ b, const double2 *__restrict__ dinv, double2 *__restrict__ x,
-           double2 *__restrict__ r, double2 *__restrict__ p, Parts part, unsigned int *counter, double *__restrict__ sc, int keep_x)
+           double2 *__restrict__ r, double2 *__restrict__ p, double *__restrict__ part_rz, double *__restrict__ part_rr,
+           unsigned int *counter, double *__restrict__ sc, int keep_x)
 {
     __shared__ double sm[VEC_BLOCK / 32];
     double rz = 0.0, rr = 0.0;
@@ -499,76 +505,274 @@ k_pcg_init(int64_t n2, const double2 *__restrict__ b, const double2 *__restrict_
         rz = fma(ri.x, zi.x, rz); rz = fma(ri.y, zi.y, rz);
         rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
     }
-    const double v[2] = {block_sum(rz, sm), block_sum(rr, sm)};
-    double t[2];
-    if (grid_sum_n<2>(v, part.p + 3, counter, sm, t) && threadIdx.x == 0) {
-        sc[SC_LOC_RZ] = t[0]; sc[SC_LOC_RR] = t[1];
-        sc[SC_DONE] = 0.0; sc[SC_IT_DONE] = 0.0;
-        if (!keep_x) sc[SC_BNORM2] = t[1];
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    double a, c;
+    if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c) && threadIdx.x == 0) { sc[0] = a; sc[1] = c; }
+}
+
+// after the (optional) all-reduce of sc[0..1]: replicate into the other parity, remember ||b||^2
+__global__ void k_pcg_init_finish(double *__restrict__ sc, int keep_x)
+{
+    sc[2] = sc[0]; sc[3] = sc[1];
+    sc[SC_DONE] = 0.0; sc[SC_IT_DONE] = 0.0;
+    if (!keep_x) sc[SC_BNORM2] = sc[1];
+}
+
+// x += alpha p ; r -= alpha q ; rz_new = r.dinv.r, rr = r.r      (alpha = rz / p.q)
+template <bool P2P>
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_update(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ p, const double2 *__restrict__ q,
+             const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r,
+             double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *counter, P2PDev pp, double *out2)
+{
+    __shared__ double sm[VEC_BLOCK / 32];
+    ring::grid_dep_wait();        // PDL: no-ops unless launched with the programmatic-serialization attribute
+    ring::grid_dep_launch();
+    if (out2 == nullptr || out2 != sc + sc_rz(it + 1)) {   // row-partitioned runs poll rarely and rely on the stop flag
+        if (sc[SC_DONE] != 0.0) return;
+    }
+    double pq, unused;
+    if (P2P) p2p_collect(pp, 0, pq, unused);
+    else pq = sc[SC_PQ];
+    const double rz_old = sc[sc_rz(it)];
+    const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 pi = p[i], qi = q[i], di = dinv[i];
+        double2 xi = x[i], ri = r[i];
+        xi.x = fma(alpha, pi.x, xi.x); xi.y = fma(alpha, pi.y, xi.y);
+        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
+        x[i] = xi; r[i] = ri;
+        const double zx = di.x * ri.x, zy = di.y * ri.y;
+        rz = fma(ri.x, zx, rz); rz = fma(ri.y, zy, rz);
+        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
+    }
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    double a, c;
+    if (grid_sum2(s1, s2, part_rz, part_rr, counter, sm, a, c)) {
+        if (P2P) p2p_publish(pp, 1, a, c);
+        else if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
     }
 }
 
-// The vector part of iteration `it` (x has received `it` updates when it starts).  With the five sums of the iteration
-//   alpha = r.z / p.q        r'.z' = r.z - 2 alpha q.z + alpha^2 q.D^-1.q        beta = r'.z' / r.z
-// one pass does  x += alpha p ;  r -= alpha q ;  p = D^-1 r + beta p  and sums r.z, r.r of the new residual directly.
-// If the current residual already meets the tolerance nothing is updated and the stop flag goes up.
-constexpr int VEC_BATCH = 2, VEC_BPS = 3;
+// p = dinv*r + beta p      (beta = rz_new / rz_old)
 template <bool P2P>
-__global__ void __launch_bounds__(VEC_BLOCK, VEC_BPS)
-k_pcg_vec(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, const double2 *__restrict__ q,
-          const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r, Parts part,
-          unsigned int *counter, P2PDev pp, double tol2)
+__global__ void __launch_bounds__(VEC_BLOCK)
+k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__restrict__ r,
+                const double2 *__restrict__ dinv, double2 *__restrict__ p, P2PDev pp, double tol2, unsigned int *done_counter)
 {
-    __shared__ double sm[VEC_BLOCK / 32];
-    ring::grid_dep_wait();        // PDL: no-op unless launched with the programmatic-serialization attribute
-    if (__ldcg(sc + SC_DONE) != 0.0) return;
-    double v[5];
+    ring::grid_dep_wait();
+    ring::grid_dep_launch();
+    if (done_counter && sc[SC_DONE] != 0.0) return;
+    double rz_new, rr;
     if (P2P) {
-        p2p_collect5(pp, v);
-        if (blockIdx.x == 0 && threadIdx.x == 0) {   // for the host poll
-#pragma unroll
-            for (int j = 0; j < 5; j++) sc[SC_PQ + j] = v[j];
-        }
+        p2p_collect(pp, 1, rz_new, rr);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr; }   // for the host poll
     } else {
-#pragma unroll
-        for (int j = 0; j < 5; j++) v[j] = __ldcg(sc + SC_PQ + j);
+        rz_new = sc[sc_rz(it + 1)];
+        rr = sc[sc_rr(it + 1)];
     }
-    if (v[SC_RR] <= tol2) {
-        // every CTA takes this branch (same five numbers everywhere) or returns above once the flag is up: x, r, p stay
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc[SC_IT_DONE] = (double)it; __threadfence(); sc[SC_DONE] = 1.0; }
+    if (done_counter && rr <= tol2) {
+        // converged by the recurrence residual: the LAST block to get here raises the flag (the others may still be reading
+        // it at their entry), so the remaining kernels of the chunk become no-ops; p is left as it is
+        __shared__ bool last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+            if (last) { sc[SC_IT_DONE] = (double)(it + 1); sc[SC_DONE] = 1.0; *done_counter = 0u; }
+        }
+        return;
+    }
+    const double rz_old = sc[sc_rz(it)];
+    const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 ri = r[i], di = dinv[i];
+        double2 pi = p[i];
+        pi.x = fma(beta, pi.x, di.x * ri.x); pi.y = fma(beta, pi.y, di.y * ri.y);
+        p[i] = pi;
+    }
+}
+
+// ---- the vector part of an iteration in ONE kernel -----------------------------------------------------------------------
+//   phase 1   r -= alpha q ; z = dinv r ; partials of r.z and r.r                 (alpha = rz / p.q)
+//   arrive    the CTA's partials are published: arrival counter; peer transport: the last CTA of this rank also writes the
+//             rank's sums into every peer's mailbox
+//   phase 2   x += alpha p                                                          (needs neither sum: hides the wait)
+//   wait      single GPU: until every CTA has arrived (all CTAs are co-resident: the grid is sized by the occupancy query),
+//             after which every CTA sums the partials in index order -- the same bits everywhere; peer transport: until the
+//             W ranks' sums are in this rank's mailbox, summed in rank order
+//   phase 3   p = z + beta p                                                        (beta = rz_new / rz)
+// A thread owns the elements tid, tid + T, tid + 2T, ... and walks them in batches with the loads of a batch issued
+// together; z of the FIRST batch stays in registers across the wait (all of z at the 1 M-cell bench size: 3 CTAs of 256
+// threads per SM own 6.07 elements per thread), the later batches re-read r and dinv.  Every vector is then read once per
+// iteration (q r dinv | p x in, r | x | p out, p a second time out of L2: 88 MB at the bench size).
+// The iteration that meets the tolerance still updates x; p is left and the stop flag goes up.
+constexpr int FUSE_BLOCK = 256, FUSE_EPT = 6, FUSE_BPS = 3;
+
+__device__ __forceinline__ void vec_phase1(int64_t n2, int64_t tid, int64_t nth, double alpha, const double2 *__restrict__ q,
+                                           const double2 *__restrict__ dinv, double2 *__restrict__ r, double2 (&zc)[FUSE_EPT],
+                                           double &rz, double &rr)
+{
+    auto residual = [&](int64_t i, double2 qi, double2 di, double2 ri) {
+        ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
+        r[i] = ri;
+        const double2 z = make_double2(di.x * ri.x, di.y * ri.y);
+        rz = fma(ri.x, z.x, rz); rz = fma(ri.y, z.y, rz);
+        rr = fma(ri.x, ri.x, rr); rr = fma(ri.y, ri.y, rr);
+        return z;
+    };
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {       // first batch: z stays in registers (the compiler interleaves the loads)
+        const int64_t i = tid + e * nth;
+        if (i < n2) zc[e] = residual(i, q[i], dinv[i], r[i]);
+    }
+    constexpr int B1 = 2;                      // later batches (large problems, DRAM-bound): loads of a batch issued together
+    for (int64_t base = tid + FUSE_EPT * nth; base < n2; base += B1 * nth) {
+        double2 qv[B1], dv[B1], rv[B1];
+#pragma unroll
+        for (int e = 0; e < B1; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) { qv[e] = q[i]; dv[e] = dinv[i]; rv[e] = r[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < B1; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) residual(i, qv[e], dv[e], rv[e]);
+        }
+    }
+}
+
+// x += alpha p over the thread's elements
+__device__ __forceinline__ void vec_phase2(int64_t n2, int64_t tid, int64_t nth, double alpha, const double2 *__restrict__ p,
+                                           double2 *__restrict__ x)
+{
+    constexpr int B2 = 3;
+    for (int64_t base = tid; base < n2; base += B2 * nth) {
+        double2 pv[B2], xv[B2];
+#pragma unroll
+        for (int e = 0; e < B2; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) { pv[e] = p[i]; xv[e] = x[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < B2; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) x[i] = make_double2(fma(alpha, pv[e].x, xv[e].x), fma(alpha, pv[e].y, xv[e].y));
+        }
+    }
+}
+
+// p = z + beta p over the thread's elements (z of the first batch from registers)
+__device__ __forceinline__ void vec_phase3(int64_t n2, int64_t tid, int64_t nth, double beta, const double2 *__restrict__ dinv,
+                                           const double2 *__restrict__ r, double2 *__restrict__ p, const double2 (&zc)[FUSE_EPT])
+{
+    {
+        double2 pv[FUSE_EPT];
+#pragma unroll
+        for (int e = 0; e < FUSE_EPT; e++) {
+            const int64_t i = tid + e * nth;
+            if (i < n2) pv[e] = p[i];
+        }
+#pragma unroll
+        for (int e = 0; e < FUSE_EPT; e++) {
+            const int64_t i = tid + e * nth;
+            if (i < n2) p[i] = make_double2(fma(beta, pv[e].x, zc[e].x), fma(beta, pv[e].y, zc[e].y));
+        }
+    }
+    constexpr int B3 = 2;   // later batches (large problems, DRAM-bound): z recomputed from r and dinv
+    for (int64_t base = tid + FUSE_EPT * nth; base < n2; base += B3 * nth) {
+        double2 pv[B3], rv[B3], dv[B3];
+#pragma unroll
+        for (int e = 0; e < B3; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) { pv[e] = p[i]; rv[e] = r[i]; dv[e] = dinv[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < B3; e++) {
+            const int64_t i = base + e * nth;
+            if (i < n2) p[i] = make_double2(fma(beta, pv[e].x, dv[e].x * rv[e].x), fma(beta, pv[e].y, dv[e].y * rv[e].y));
+        }
+    }
+}
+
+// n_pq_part > 0 (single GPU, ring SpMV): p.q = sum of the SpMV's per-CTA partials part_pq[0 .. n_pq_part), added up here by
+// every CTA in the same order; otherwise sc[SC_PQ] (row kernel) or the peers' mailboxes (P2P).
+// `barrier` counts arrivals monotonically (zeroed by the host); `target` = arrivals once every CTA of THIS launch is in.
+template <bool P2P>
+__global__ void __launch_bounds__(FUSE_BLOCK, FUSE_BPS)
+k_pcg_vec(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, const double2 *__restrict__ q,
+          const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ r, const double *__restrict__ part_pq,
+          int n_pq_part, double *__restrict__ part_rz, double *__restrict__ part_rr, unsigned int *barrier, unsigned int target,
+          P2PDev pp, double tol2, int *err)
+{
+    __shared__ double sm[FUSE_BLOCK / 32];
+    __shared__ bool is_last;
+    ring::grid_dep_wait();        // PDL: no-op unless launched with the programmatic-serialization attribute
+    if (__ldcg(sc + SC_DONE) != 0.0 || *reinterpret_cast<volatile int *>(err)) return;   // stopped, or an earlier wait timed out
+    double pq, unused;
+    if (P2P) p2p_collect(pp, 0, pq, unused);
+    else if (n_pq_part > 0) {
+        double a = 0.0;
+        for (int j = threadIdx.x; j < n_pq_part; j += blockDim.x) a += __ldcg(part_pq + j);
+        pq = block_sum(a, sm);
+    } else pq = __ldcg(sc + SC_PQ);
+    const double rz_old = __ldcg(sc + sc_rz(it));
+    const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    double2 zc[FUSE_EPT];
+    double rz = 0.0, rr = 0.0;
+    vec_phase1(n2, tid, nth, alpha, q, dinv, r, zc, rz, rr);
+    const double s1 = block_sum(rz, sm);
+    const double s2 = block_sum(rr, sm);
+    // arrive
+    if (threadIdx.x == 0) {
+        part_rz[blockIdx.x] = s1; part_rr[blockIdx.x] = s2;
+        __threadfence();
+        is_last = (atomicAdd(barrier, 1u) + 1u == target);
+    }
+    if (P2P) {
+        __syncthreads();
+        if (is_last) {            // this rank's sums -> every peer's mailbox
+            __threadfence();
+            double a = 0.0, c = 0.0;
+            for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) { a += __ldcg(part_rz + j); c += __ldcg(part_rr + j); }
+            const double t1 = block_sum(a, sm), t2 = block_sum(c, sm);
+            p2p_publish(pp, 1, t1, t2);
+        }
+    }
+    vec_phase2(n2, tid, nth, alpha, p, x);
+    // wait
+    double rz_new, rr_new;
+    if (P2P) p2p_collect(pp, 1, rz_new, rr_new);
+    else {
+        if (threadIdx.x == 0) {
+            long long t0 = 0;
+            for (unsigned spins = 0; *reinterpret_cast<volatile unsigned int *>(barrier) < target; spins++) {
+                if ((spins & 0xffff) == 0xffff) {      // a CTA that never became resident: give up instead of hanging
+                    const long long now = clock64();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > P2P_TIMEOUT_CLOCKS) { *err = 1; break; }
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        double a = 0.0, c = 0.0;
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) { a += __ldcg(part_rz + j); c += __ldcg(part_rr + j); }
+        rz_new = block_sum(a, sm); rr_new = block_sum(c, sm);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc[sc_rz(it + 1)] = rz_new; sc[sc_rr(it + 1)] = rr_new; }
+    if (rr_new <= tol2) {
+        // converged by the recurrence residual: every CTA sees the same two numbers and leaves p alone; the flag turns the rest
+        // of the enqueued chunk into no-ops
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc[SC_IT_DONE] = (double)(it + 1); __threadfence(); sc[SC_DONE] = 1.0; }
         return;
     }
     ring::grid_dep_launch();      // the next SpMV may become resident from here on (its producer warp pre-fills the ring)
-    const double pq = v[SC_PQ], rz = v[SC_RZ];
-    const double alpha = (pq != 0.0) ? rz / pq : 0.0;
-    const double rz_next = fma(alpha, fma(alpha, v[SC_QDQ], -2.0 * v[SC_QZ]), rz);
-    const double beta = (rz != 0.0 && rz_next > 0.0) ? rz_next / rz : 0.0;
-    double s_rz = 0.0, s_rr = 0.0;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = tid; base < n2; base += VEC_BATCH * nth) {
-        double2 pv[VEC_BATCH], qv[VEC_BATCH], dv[VEC_BATCH], xv[VEC_BATCH], rv[VEC_BATCH];
-#pragma unroll
-        for (int e = 0; e < VEC_BATCH; e++) {
-            const int64_t i = base + e * nth;
-            if (i < n2) { qv[e] = q[i]; rv[e] = r[i]; dv[e] = dinv[i]; pv[e] = p[i]; xv[e] = x[i]; }
-        }
-#pragma unroll
-        for (int e = 0; e < VEC_BATCH; e++) {
-            const int64_t i = base + e * nth;
-            if (i < n2) {
-                const double2 rn = make_double2(fma(-alpha, qv[e].x, rv[e].x), fma(-alpha, qv[e].y, rv[e].y));
-                const double2 z = make_double2(dv[e].x * rn.x, dv[e].y * rn.y);
-                x[i] = make_double2(fma(alpha, pv[e].x, xv[e].x), fma(alpha, pv[e].y, xv[e].y));
-                r[i] = rn;
-                p[i] = make_double2(fma(beta, pv[e].x, z.x), fma(beta, pv[e].y, z.y));
-                s_rz = fma(rn.x, z.x, s_rz); s_rz = fma(rn.y, z.y, s_rz);
-                s_rr = fma(rn.x, rn.x, s_rr); s_rr = fma(rn.y, rn.y, s_rr);
-            }
-        }
-    }
-    const double bs[2] = {block_sum(s_rz, sm), block_sum(s_rr, sm)};
-    double t[2];
-    if (grid_sum_n<2>(bs, part.p + 3, counter, sm, t) && threadIdx.x == 0) { sc[SC_LOC_RZ] = t[0]; sc[SC_LOC_RR] = t[1]; }
+    const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    vec_phase3(n2, tid, nth, beta, dinv, r, p, zc);
 }
 
 // r = b - q (true residual), rr_true = r.r
@@ -636,6 +840,7 @@ static cudaError_t all_reduce(const DistPlan *d, double *v, int count, cudaStrea
     NCCL_OK(nc->AllReduce(src ? src : v, v, (size_t)count, ncclDouble, ncclSum, d->comm, s));
     return cudaSuccess;
 }
+
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
@@ -657,29 +862,22 @@ static int spmv_grid(int64_t n_node)
 }
 
 static const P2PDev NO_P2P{nullptr, nullptr, 1, 0, 0.0, 0, nullptr, 0u};
-static Parts parts_of(const PcgBuffers &w)
-{
-    Parts pt;
-    for (int j = 0; j < 5; j++) pt.p[j] = w.part[j];
-    return pt;
-}
 
-// plain launch: ghosts (if any) are the tail of x.  MODE 0 product, MODE 1 product and x.y -> *out
-template <int MODE>
-static void launch_spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, const PcgBuffers *w, unsigned int *counter,
-                        double *out, cudaStream_t s)
+// plain launch: ghosts (if any) are the tail of x
+template <bool DOT>
+static void launch_spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, double *part, unsigned int *counter,
+                        double *dot_out, cudaStream_t s, const double *done = nullptr)
 {
     const int64_t n_node = A.n_own / 2;
-    k_spmv<MODE, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, nullptr, nullptr,
-                                                                  w ? parts_of(*w) : Parts{}, counter, nullptr, out, NO_P2P, 0, nullptr,
-                                                                  nullptr, nullptr, 0, HaloPush{});
+    k_spmv<DOT, false><<<spmv_grid(n_node), SPMV_BLOCK, 0, s>>>(n_node, A.node_ptr, A.node_idx, A.data, x, y, fixed, part, counter,
+                                                                 dot_out, NO_P2P, 0, nullptr, nullptr, nullptr, 0, HaloPush{}, done);
 }
 
 // y = K x on the rows this rank owns (all rows on a single GPU); x must hold current ghost values
 cudaError_t spmv(const DevSystem &A, const double *x, double *y, const uint8_t *fixed, cudaStream_t s)
 {
     if (A.n_own == 0) return cudaSuccess;
-    launch_spmv<0>(A, x, y, fixed, nullptr, nullptr, nullptr, s);
+    launch_spmv<false>(A, x, y, fixed, nullptr, nullptr, nullptr, s);
     return cudaGetLastError();
 }
 
@@ -750,8 +948,8 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
     const int64_t n_own = A.n_own;
     cudaError_t e = halo_exchange(dist, w.x, w.x + n_own, s, launches);
     if (e != cudaSuccess) return e;
-    launch_spmv<0>(A, w.x, w.q, fixed, nullptr, nullptr, nullptr, s);
-    k_true_residual<<<vec_grid(n_own), VEC_BLOCK, 0, s>>>(n_own, w.b, w.q, w.r, w.part[4], w.counters + 2, w.sc + SC_RR_TRUE);
+    launch_spmv<false>(A, w.x, w.q, fixed, nullptr, nullptr, nullptr, s);
+    k_true_residual<<<vec_grid(n_own), VEC_BLOCK, 0, s>>>(n_own, w.b, w.q, w.r, w.part_b, w.counters + 2, w.sc + SC_RR_TRUE);
     if (launches) *launches += 2;
     if ((e = all_reduce(dist, w.sc + SC_RR_TRUE, 1, s)) != cudaSuccess) return e;
     e = cudaMemcpyAsync(rr_true, w.sc + SC_RR_TRUE, sizeof(double), cudaMemcpyDeviceToHost, s);
@@ -760,22 +958,23 @@ static cudaError_t true_residual(const DevSystem &A, const uint8_t *fixed, PcgBu
 }
 
 // Runs PCG; returns via info.  `chunk` iterations are enqueued between host polls (the device stops on its own).
-// prof (optional): 2 pools of 4*chunk events; prof_ms[0..1] accumulate the device time of the SpMV (incl. halo exchange
-// and the all-reduce when row-partitioned) / the vector kernel of every prof_every-th iteration, prof_ms[3] the iterations
-// profiled.  The events of a chunk are read back while the next chunk runs, so profiling does not stall the GPU.
+// prof (optional): 2 pools of 4*chunk events; prof_ms[0..2] accumulate the device time of the SpMV (incl. halo exchange and the
+// p.q all-reduce when row-partitioned) / the vector kernel (NCCL transport: update / direction kernels) of every
+// prof_every-th iteration, prof_ms[3] the iterations profiled.  The events of a chunk are read back while the next chunk
+// runs, so profiling does not stall the GPU.
 //
 // Row-partitioned, two transports:
-//   NCCL  -- per iteration: pack + ncclSend/Recv of the ghost entries of p, ONE ncclAllReduce of the five sums
+//   NCCL  -- per iteration: pack + ncclSend/Recv of the ghost entries of p, ncclAllReduce(p.q), ncclAllReduce(rz, rr)
 //   peer  -- (dist->p2p) no NCCL call inside the loop: CTA 0 of the SpMV writes this rank's boundary entries of p into the
 //            neighbours' ghost segments over NVLink, the rows that gather ghosts wait for the neighbours' stamps; the last
-//            CTA of the SpMV writes the five sums into every peer's mailbox and the vector kernel adds the W contributions
-//            in rank order.  The first iteration after (re)initialisation still uses NCCL for the halo.
+//            CTA of the SpMV / of the vector kernel's first phase writes its sums into every peer's mailbox and the consumer
+//            adds the W contributions in rank order.  The first iteration after (re)initialisation still uses NCCL for the halo.
 cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, DistPlan *dist, double rtol, int maxit,
                     int chunk, mofem_solve_info_t *info, cudaStream_t s, int64_t *launches, cudaEvent_t *prof, double *prof_ms, int prof_every)
 {
     if (prof_every < 1) prof_every = 1;
     const int64_t n_own = A.n_own, n_node = n_own / 2, n2 = n_own / 2;
-    const int gv = vec_grid(n2, 148 * VEC_BPS), gs = spmv_grid(n_node);
+    const int gv = vec_grid(n2), gs = spmv_grid(n_node);
     cudaError_t e;
     double sc_host[SC_COUNT];
     const double2 *b2 = reinterpret_cast<const double2 *>(w.b), *dinv2 = reinterpret_cast<const double2 *>(w.dinv);
@@ -786,7 +985,6 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
     const int W = dist ? dist->world : 1;
     const double stamp0 = peer ? (double)(++dist->epoch) * 4294967296.0 : 0.0;
     int *err_dev = reinterpret_cast<int *>(w.counters + 6);
-    const Parts parts = parts_of(w);
     auto ppdev = [&](int it_for) {
         P2PDev pp = NO_P2P;
         if (peer) {
@@ -797,12 +995,11 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
         return pp;
     };
     auto init = [&](int keep_x) -> cudaError_t {
-        k_pcg_init<<<vec_grid(n2), VEC_BLOCK, 0, s>>>(n2, b2, dinv2, x2, r2, p2, parts, w.counters + 1, w.sc, keep_x);
-        if (launches) ++*launches;
-        if (!keep_x) {   // |b|^2 over all ranks (once per solve)
-            const cudaError_t ee = all_reduce(dist, w.sc + SC_BNORM2, 1, s);
-            if (ee != cudaSuccess) return ee;
-        }
+        k_pcg_init<<<gv, VEC_BLOCK, 0, s>>>(n2, b2, dinv2, x2, r2, p2, w.part_a, w.part_b, w.counters + 1, w.sc, keep_x);
+        cudaError_t ee = all_reduce(dist, w.sc, 2, s);
+        if (ee != cudaSuccess) return ee;
+        k_pcg_init_finish<<<1, 1, 0, s>>>(w.sc, keep_x);
+        if (launches) *launches += 2;
         return cudaGetLastError();
     };
     if ((e = init(0)) != cudaSuccess) return e;
@@ -817,7 +1014,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
         return cudaSuccess;
     }
     const double tol2 = rtol * rtol * bnorm2;
-    int it = 0;       // updates x has received
+    int it = 0;       // global iteration counter (parity selects the (rz, rr) pair)
     double prev_rr_true = 0.0;
     bool fresh = true;   // p was just (re)initialised: its halo has not been pushed by a previous iteration
     int pend_pool = -1, pend_n = 0, pool = 0;
@@ -825,7 +1022,7 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
         if (!prof || pend_pool < 0) return;
         cudaEvent_t *ev = prof + (size_t)pend_pool * 4 * chunk;
         for (int k = 0; k < pend_n; k++)
-            for (int j = 0; j < 2; j++) {
+            for (int j = 0; j < 3; j++) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, ev[4 * k + j], ev[4 * k + j + 1]);
                 prof_ms[j] += ms;
@@ -840,14 +1037,30 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
     const bool ring_on = (single || peer) && w.use_ring && w.n_tile > 0;
     if (ring_on) {
         // per device (a process may hold contexts on several GPUs), so set on every solve: microseconds
-        if ((e = cudaFuncSetAttribute(k_spmv_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_spmv_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_spmv_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_spmv_ring_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, PcgRing::SMEM_BYTES)) != cudaSuccess) return e;
     }
+    // the vector kernel waits inside the kernel for all its CTAs (grid barrier) or for the peers: every CTA must be resident
+    int g_vec = 0;
+    if (single || peer) {
+        int bps = 0;
+        const cudaError_t oe = single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_vec<false>, FUSE_BLOCK, 0)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg_vec<true>, FUSE_BLOCK, 0);
+        if (oe != cudaSuccess || bps < 1) return oe != cudaSuccess ? oe : cudaErrorLaunchOutOfResources;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t want = (n2 + FUSE_BLOCK - 1) / FUSE_BLOCK, cap = (int64_t)sms * std::min(bps, FUSE_BPS);
+        g_vec = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, cap), PCG_MAX_PART));
+        if ((e = cudaMemsetAsync(w.counters + 4, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+    }
+    unsigned int vec_k = 0;    // vector-kernel launches since the arrival counter was last zeroed
     // programmatic dependent launch between the kernels of the loop; measured: costs time with the row kernel
     // (181 vs 133 us per iteration), and a run that times every iteration wants the kernels back to back
     const bool pdl = (single || peer) && w.use_pdl && ring_on && !(prof && prof_every == 1);
     const int g_ring = w.n_tile < RING_GRID ? w.n_tile : RING_GRID;
     const RingTile *tiles = reinterpret_cast<const RingTile *>(w.ring_tiles);
+    const double *done_flag = w.sc + SC_DONE;
     while (it < maxit) {
         int todo = chunk;
         if (it + todo > maxit) todo = maxit - it;
@@ -859,72 +1072,82 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
             const int k = n_sampled;
             if (ev) { n_sampled++; cudaEventRecord(ev[4 * k], s); }
             const P2PDev pp = ppdev(it);
-            if (!peer) {
-                if (multi && (e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
-                if (ring_on)
-                    e = launch_ex(pdl, k_spmv_ring<false>, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile, tiles, A.node_ptr,
-                                  A.node_idx, A.data, (const double *)w.p, w.q, fixed, (const double *)w.r, (const double *)w.dinv, parts,
-                                  w.counters, w.sc, NO_P2P, 0, (const int *)nullptr, (const uint8_t *)nullptr, (const int32_t *)nullptr,
-                                  (int64_t)0, HaloPush{});
-                else
-                    e = launch_ex(false, k_spmv<2, false>, gs, SPMV_BLOCK, 0, s, n_node, A.node_ptr, A.node_idx, A.data, (const double *)w.p,
-                                  w.q, fixed, (const double *)w.r, (const double *)w.dinv, parts, w.counters, w.sc,
-                                  w.sc + (multi ? SC_PART : SC_PQ), NO_P2P, 0, (const int *)nullptr, (const uint8_t *)nullptr,
-                                  (const int32_t *)nullptr, (int64_t)0, HaloPush{});
-                if (e != cudaSuccess) return done(e);
-                // NCCL: the partial sums are all-reduced INTO the global slots, so re-reducing after the device has stopped is idempotent
-                if (multi && (e = all_reduce(dist, w.sc + SC_PQ, 5, s, w.sc + SC_PART)) != cudaSuccess) return done(e);
-            } else {
-                HaloPush hp{};
-                if (fresh) {   // halo of a freshly initialised p: NCCL, nothing to push or to wait for
-                    if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
+            if (single || peer) {
+                if (single) {
+                    if (ring_on)
+                        e = launch_ex(pdl, k_spmv_ring, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile, tiles, A.node_ptr, A.node_idx,
+                                      A.data, (const double *)w.p, w.q, fixed, w.part_c, done_flag);
+                    else
+                        e = launch_ex(false, k_spmv<true, false>, gs, SPMV_BLOCK, 0, s, n_node, A.node_ptr, A.node_idx, A.data, (const double *)w.p,
+                                      w.q, fixed, w.part_c, w.counters, w.sc + SC_PQ, NO_P2P, 0, (const int *)nullptr, (const uint8_t *)nullptr,
+                                      (const int32_t *)nullptr, (int64_t)0, HaloPush{}, done_flag);
                 } else {
-                    hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
-                    hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb;
+                    HaloPush hp{};
+                    if (fresh) {   // halo of a freshly initialised p: NCCL, nothing to push or to wait for
+                        if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
+                    } else {
+                        hp.n_send = n_send; hp.send_idx = dist->send_idx; hp.send_nb = dist->send_nb; hp.send_dst = dist->send_dst;
+                        hp.nb_ghost_off = dist->nb_ghost_off; hp.nb_rank = dist->nb_rank_dev; hp.n_nb = n_nb;
+                    }
+                    const int n_wait = fresh ? 0 : dist->n_wait;
+                    if (ring_on)
+                        e = launch_ex(pdl && !fresh, k_spmv_ring_p2p, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile, tiles, n_node,
+                                      A.node_ptr, A.node_idx, A.data, (const double *)w.p, w.q, fixed, w.part_c, w.counters, pp, n_wait,
+                                      (const int *)dist->wait_rank, (const uint8_t *)w.row_halo, (const int32_t *)dist->halo_rows,
+                                      dist->n_halo_rows, hp, done_flag);
+                    else
+                        e = launch_ex(false, k_spmv<true, true>, gs, SPMV_BLOCK, 0, s, n_node, A.node_ptr, A.node_idx, A.data, (const double *)w.p,
+                                      w.q, fixed, w.part_c, w.counters, (double *)nullptr, pp, n_wait, (const int *)dist->wait_rank,
+                                      (const uint8_t *)w.row_halo, (const int32_t *)dist->halo_rows, dist->n_halo_rows, hp, done_flag);
+                    fresh = false;
                 }
-                const int n_wait = fresh ? 0 : dist->n_wait;
-                if (ring_on)
-                    e = launch_ex(pdl && !fresh, k_spmv_ring<true>, g_ring, PcgRing::THREADS, PcgRing::SMEM_BYTES, s, w.n_tile, tiles, A.node_ptr,
-                                  A.node_idx, A.data, (const double *)w.p, w.q, fixed, (const double *)w.r, (const double *)w.dinv, parts,
-                                  w.counters, w.sc, pp, n_wait, (const int *)dist->wait_rank, (const uint8_t *)w.row_halo,
-                                  (const int32_t *)dist->halo_rows, dist->n_halo_rows, hp);
-                else
-                    e = launch_ex(false, k_spmv<2, true>, gs, SPMV_BLOCK, 0, s, n_node, A.node_ptr, A.node_idx, A.data, (const double *)w.p, w.q,
-                                  fixed, (const double *)w.r, (const double *)w.dinv, parts, w.counters, w.sc, (double *)nullptr, pp, n_wait,
-                                  (const int *)dist->wait_rank, (const uint8_t *)w.row_halo, (const int32_t *)dist->halo_rows,
-                                  dist->n_halo_rows, hp);
                 if (e != cudaSuccess) return done(e);
-                fresh = false;
+                if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                if ((uint64_t)(vec_k + 1) * (uint64_t)g_vec > 0x7fffffffull) {   // keep the arrival counter inside 32 bits
+                    if ((e = cudaMemsetAsync(w.counters + 4, 0, sizeof(unsigned int), s)) != cudaSuccess) return done(e);
+                    vec_k = 0;
+                }
+                ++vec_k;
+                const unsigned int target = vec_k * (unsigned int)g_vec;
+                if (single)
+                    e = launch_ex(pdl, k_pcg_vec<false>, g_vec, FUSE_BLOCK, 0, s, n2, it, w.sc, p2, (const double2 *)q2, dinv2, x2, r2,
+                                  (const double *)w.part_c, ring_on ? g_ring : 0, w.part_a, w.part_b, w.counters + 4, target, NO_P2P, tol2, err_dev);
+                else
+                    e = launch_ex(pdl, k_pcg_vec<true>, g_vec, FUSE_BLOCK, 0, s, n2, it, w.sc, p2, (const double2 *)q2, dinv2, x2, r2,
+                                  (const double *)w.part_c, 0, w.part_a, w.part_b, w.counters + 4, target, pp, tol2, err_dev);
+                if (e != cudaSuccess) return done(e);
+                if (ev) { cudaEventRecord(ev[4 * k + 2], s); cudaEventRecord(ev[4 * k + 3], s); }
+            } else {
+                // NCCL transport: partials are all-reduced INTO the global slots, so re-reducing after the device has stopped is idempotent
+                if ((e = halo_exchange(dist, w.p, w.p + n_own, s, launches)) != cudaSuccess) return done(e);
+                launch_spmv<true>(A, w.p, w.q, fixed, w.part_c, w.counters, w.sc + SC_PART_PQ, s, done_flag);
+                if ((e = all_reduce(dist, w.sc + SC_PQ, 1, s, w.sc + SC_PART_PQ)) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 1], s);
+                k_pcg_update<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, p2, q2, dinv2, x2, r2, w.part_a, w.part_b,
+                                                            w.counters + 1, NO_P2P, w.sc + SC_PART_RZ);
+                if ((e = all_reduce(dist, w.sc + sc_rz(it + 1), 2, s, w.sc + SC_PART_RZ)) != cudaSuccess) return done(e);
+                if (ev) cudaEventRecord(ev[4 * k + 2], s);
+                k_pcg_direction<false><<<gv, VEC_BLOCK, 0, s>>>(n2, it, w.sc, r2, dinv2, p2, NO_P2P, tol2, w.counters + 5);
+                if (ev) cudaEventRecord(ev[4 * k + 3], s);
             }
-            if (ev) cudaEventRecord(ev[4 * k + 1], s);
-            if (peer)
-                e = launch_ex(pdl, k_pcg_vec<true>, gv, VEC_BLOCK, 0, s, n2, it, w.sc, p2, (const double2 *)q2, dinv2, x2, r2, parts,
-                              w.counters + 1, pp, tol2);
-            else
-                e = launch_ex(pdl, k_pcg_vec<false>, gv, VEC_BLOCK, 0, s, n2, it, w.sc, p2, (const double2 *)q2, dinv2, x2, r2, parts,
-                              w.counters + 1, NO_P2P, tol2);
-            if (e != cudaSuccess) return done(e);
-            if (ev) cudaEventRecord(ev[4 * k + 2], s);
         }
-        if (launches) *launches += 2 * (int64_t)todo;
+        if (launches) *launches += ((single || peer) ? 2 : 3) * (int64_t)todo;
         harvest();  // events of the previous chunk, while this one runs
         e = cudaMemcpyAsync(sc_host, w.sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
         int err_host = 0;
-        if (peer) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (single || peer) e = cudaMemcpyAsync(&err_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) return done(e);
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return done(e);
-        if (err_host) return done(cudaErrorLaunchTimeout);   // a peer did not answer within P2P_TIMEOUT_CLOCKS (~20 s)
+        if (err_host) return done(cudaErrorLaunchTimeout);   // a peer (or a CTA of the grid barrier) did not answer within P2P_TIMEOUT_CLOCKS (~20 s)
         if (prof) { pend_pool = pool; pend_n = n_sampled; pool ^= 1; }
-        const bool stopped = sc_host[SC_DONE] != 0.0;
-        if (stopped) it = (int)sc_host[SC_IT_DONE];   // the device stopped inside the chunk: x has `it` updates
+        if (sc_host[SC_DONE] != 0.0) it = (int)sc_host[SC_IT_DONE];   // the device stopped early inside the chunk
         info->iterations = it;
-        // r.r over all ranks as the last vector kernel that ran saw it (the residual BEFORE its update, or the one that stopped it)
-        const double rr = sc_host[SC_RR];
+        const double rr = sc_host[sc_rr(it)];
         info->relres_rec = sqrt(rr / bnorm2);
         if (!(rr == rr)) break;  // NaN: breakdown
-        if (stopped) {
+        if (rr <= tol2) {
             // recurrence residual says converged: verify with the true residual r = b - A x
             double rr_true;
             e = true_residual(A, fixed, w, dist, s, &rr_true, launches);
@@ -944,8 +1167,13 @@ cudaError_t pcg_run(const DevSystem &A, const uint8_t *fixed, PcgBuffers &w, Dis
             prev_rr_true = rr_true;
             info->restarts++;
             if (info->restarts > 20) break;
-            if ((e = init(1)) != cudaSuccess) return done(e);
+            if ((e = init(1)) != cudaSuccess) return done(e);  // publishes rz in both parity slots, lowers the stop flag
             fresh = true;
+            // the launches behind the one that raised the flag left without arriving: realign the arrival counter
+            if (g_vec) {
+                if ((e = cudaMemsetAsync(w.counters + 4, 0, sizeof(unsigned int), s)) != cudaSuccess) return done(e);
+                vec_k = 0;
+            }
         }
     }
     // not converged by the recurrence test: report the true residual anyway
@@ -969,7 +1197,7 @@ cudaError_t pcg_finish(const DevSystem &A, PcgBuffers &w, const DistPlan *dist, 
 // u^T K u  (the caller halves it); u must hold current ghost values
 cudaError_t energy_of(const DevSystem &A, const double *u, PcgBuffers &w, const DistPlan *dist, double *out_dev, cudaStream_t s)
 {
-    launch_spmv<1>(A, u, w.q, nullptr, &w, w.counters + 3, out_dev, s);
+    launch_spmv<true>(A, u, w.q, nullptr, w.part_c, w.counters + 3, out_dev, s);
     cudaError_t e = all_reduce(dist, out_dev, 1, s);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

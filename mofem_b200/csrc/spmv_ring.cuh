@@ -10,8 +10,12 @@
 //     access left is the gather of x, which lives in L2/L1), and arrive on "empty" to hand the stage back.
 // Warps move through the ring independently, so up to STAGES tiles per CTA are in flight regardless of what the
 // consumers are doing.  With PDL the producer fills the ring's STAGES stages before the previous kernel of the PCG iteration
-// has finished (the matrix does not depend on it); everything else waits for the grid dependency.
-// The consumers also accumulate, for the rows they produce, the three sums the single-reduction PCG needs (RingDots).
+// has finished (the matrix does not depend on it); then both sides order themselves behind that kernel and look at the
+// solver's stop flag -- if it is up, the producer lets its copies land and the whole CTA leaves (a no-op SpMV costs
+// microseconds, not a pass over the matrix).
+// Measured on the 1 M-cell bench matrix (ncu, kernels in sequence, warm L2): 82.9 us = 5.6 TB/s of DRAM traffic.  Things that
+// were tried and made it slower are listed in DESIGN.md (staging the rows' vector entries through the ring, explicit
+// ld.shared addressing, three fused dot products instead of one).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,7 +27,7 @@ struct alignas(16) RingTile {
     int32_t a0, a1;   // node rows [a0, a1)
     int64_t flags;    // bit 0: some row of the tile is masked (row_skip), consumers then test every row
 };
-static_assert(sizeof(RingTile) == 32, "RingTile is read as two 16-byte words");
+static_assert(sizeof(RingTile) == 32, "RingTile is read as 16-byte words");
 
 template <int SPAN_, int MAXDEG_, int STAGES_, int CW_, bool EVICT_FIRST_ = true>
 struct RingCfg {
@@ -83,116 +87,84 @@ __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.w
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 }  // namespace ring
 
-// Sums the PCG loop needs from the SpMV (single-reduction CG, pcg.cu): with q = K p, z = D^-1 r
-//   pq = p.q     qz = q.z     qdq = q.D^-1.q
-struct RingDots { double pq, qz, qdq; };
-__device__ __forceinline__ void ring_row_dots(RingDots &d, double2 pa, double2 ra, double2 da, double y0, double y1)
-{
-    const double t0 = da.x * y0, t1 = da.y * y1;
-    d.pq = fma(pa.x, y0, d.pq); d.pq = fma(pa.y, y1, d.pq);
-    d.qz = fma(t0, ra.x, d.qz); d.qz = fma(t1, ra.y, d.qz);
-    d.qdq = fma(t0, y0, d.qdq); d.qdq = fma(t1, y1, d.qdq);
-}
-
-// State of the producer lane between ring_prologue and ring_main.
-struct RingState { int k, t; bool active; };
-
-// one tile -> stage s of the ring: header + three bulk copies (values, column indices, row pointers) on full[s]
-template <class Cfg>
-__device__ __forceinline__ void ring_issue(unsigned char *smem, uint64_t *full, int s, int t, const RingTile *__restrict__ tiles,
-                                           const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
-                                           const double *__restrict__ data, uint64_t pol)
-{
-    unsigned char *st = smem + s * Cfg::STAGE_BYTES;
-    const longlong2 h0 = __ldg(reinterpret_cast<const longlong2 *>(tiles + t));
-    const longlong2 h1 = __ldg(reinterpret_cast<const longlong2 *>(tiles + t) + 1);   // {a0, a1 | flags}
-    *reinterpret_cast<longlong2 *>(st + Cfg::HDR_OFF) = h0;
-    *reinterpret_cast<longlong2 *>(st + Cfg::HDR_OFF + 16) = h1;
-    const int64_t b0 = h0.x, b1 = h0.y;
-    const int a0 = (int)(h1.x & 0xffffffffll), a1 = (int)(h1.x >> 32);
-    const int64_t i0 = b0 & ~(int64_t)3;
-    const int p0 = a0 & ~1;
-    const uint32_t bytes_v = (uint32_t)(b1 - b0) * 32u;
-    const uint32_t bytes_i = bytes_v ? (((uint32_t)(b1 - i0) * 4u + 15u) & ~15u) : 0u;
-    const uint32_t bytes_p = ((uint32_t)(a1 + 1 - p0) * 8u + 15u) & ~15u;
-    ring::mbar_arrive_tx(&full[s], bytes_v + bytes_i + bytes_p);
-    if (bytes_v) {
-        if (Cfg::EVICT_FIRST) {
-            ring::bulk_g2s_hint(st + Cfg::VAL_OFF, data + 4 * b0, bytes_v, &full[s], pol);
-            ring::bulk_g2s_hint(st + Cfg::IDX_OFF, node_idx + i0, bytes_i, &full[s], pol);
-        } else {
-            ring::bulk_g2s(st + Cfg::VAL_OFF, data + 4 * b0, bytes_v, &full[s]);
-            ring::bulk_g2s(st + Cfg::IDX_OFF, node_idx + i0, bytes_i, &full[s]);
-        }
-    }
-    ring::bulk_g2s(st + Cfg::PTR_OFF, node_ptr + p0, bytes_p, &full[s]);
-}
-
-// First half of the ring SpMV: mbarrier set-up, the producer lane streams the CTA's first STAGES tiles BEFORE the grid
-// dependency (the matrix does not depend on the previous kernel), then every thread orders itself behind the previous kernel
-// (griddepcontrol.wait: a no-op without the programmatic-serialization launch attribute) and looks at the stop flag.  When the
-// flag is up the producer waits for its copies to land (a CTA must not exit with bulk copies in flight) and the caller
-// returns: active == false.
-template <class Cfg>
-__device__ __forceinline__ RingState ring_prologue(unsigned char *smem, int n_tile, const RingTile *__restrict__ tiles,
-                                                   const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
-                                                   const double *__restrict__ data, const double *done_flag)
-{
-    constexpr int S = Cfg::STAGES, CW = Cfg::CW;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * Cfg::STAGE_BYTES);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) { ring::mbar_init(&full[s], 1); ring::mbar_init(&full[S + s], CW); }   // full[S + s] = empty[s]
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    RingState rs;
-    rs.k = 0; rs.t = blockIdx.x;
-    const bool producer = (warp == CW && lane == 0);
-    if (producer) {
-        const uint64_t pol = Cfg::EVICT_FIRST ? ring::policy_evict_first() : 0;
-        for (; rs.k < S && rs.t < n_tile; rs.k++, rs.t += gridDim.x) ring_issue<Cfg>(smem, full, rs.k, rs.t, tiles, node_ptr, node_idx, data, pol);
-    }
-    ring::grid_dep_wait();
-    rs.active = !(done_flag && __ldcg(done_flag) != 0.0);
-    if (!rs.active && producer)
-        for (int s = 0; s < rs.k; s++) ring::mbar_wait(&full[s], 0);
-    return rs;
-}
-
-// Second half: the producer lane keeps the ring full, the consumer warps compute y = K x on node rows out of shared memory
-// (fixed rows -> 0) and accumulate the three sums of the PCG loop for their rows (lanes with sub == 0).
+// y = K x on node rows (fixed rows -> 0); returns this thread's share of x.y in `dot` (consumer lanes with sub == 0).
 // MASKED: rows with row_skip[row] != 0 are left out (their tiles carry flag bit 0).
-// Called by every thread of a CTA of Cfg::THREADS threads with Cfg::SMEM_BYTES of dynamic shared memory, after ring_prologue.
+// done_flag (may be null): the solver's stop flag, read behind the grid dependency; returns false (nothing computed, every
+// thread of the CTA) when it is up.
+// Called by every thread of a CTA of Cfg::THREADS threads with Cfg::SMEM_BYTES of dynamic shared memory.
 // node_idx must be readable up to 12 bytes and node_ptr up to 8 bytes past their ends (the copies are 16-byte granular).
-template <class Cfg, bool MASKED = false>
-__device__ __forceinline__ void ring_main(unsigned char *smem, RingState rs, int n_tile, const RingTile *__restrict__ tiles,
-                                          const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
-                                          const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
-                                          const uint8_t *__restrict__ fixed, const double *__restrict__ r,
-                                          const double *__restrict__ dinv, RingDots &dots,
-                                          const uint8_t *__restrict__ row_skip = nullptr)
+template <class Cfg, bool TRIG_LATE = false, bool MASKED = false>
+__device__ __forceinline__ bool ring_spmv_body(unsigned char *smem, int n_tile, const RingTile *__restrict__ tiles,
+                                               const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ node_idx,
+                                               const double *__restrict__ data, const double *__restrict__ x,
+                                               double *__restrict__ y, const uint8_t *__restrict__ fixed, double &dot,
+                                               const uint8_t *__restrict__ row_skip = nullptr, const double *done_flag = nullptr)
 {
     constexpr int S = Cfg::STAGES, CW = Cfg::CW;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + S * Cfg::STAGE_BYTES);
     uint64_t *empty = full + S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { ring::mbar_init(&full[s], 1); ring::mbar_init(&empty[s], CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     if (warp == CW) {
+        // ---- producer: the matrix does not depend on the previous kernel, so the first STAGES tiles stream before the grid
+        // dependency; the header of the next tile is fetched BEFORE the wait for its stage, so the copies go out the moment the
+        // consumers hand the stage back
         if (lane == 0) {
             const uint64_t pol = Cfg::EVICT_FIRST ? ring::policy_evict_first() : 0;
-            int k = rs.k;
-            for (int t = rs.t; t < n_tile; t += gridDim.x, k++) {
+            int k = 0;
+            for (int t = blockIdx.x; t < n_tile; t += gridDim.x, k++) {
                 const int s = k % S;
-                ring::mbar_wait(&empty[s], ((k / S) - 1) & 1);
-                ring_issue<Cfg>(smem, full, s, t, tiles, node_ptr, node_idx, data, pol);
+                unsigned char *st = smem + s * Cfg::STAGE_BYTES;
+                const longlong2 h0 = __ldg(reinterpret_cast<const longlong2 *>(tiles + t));
+                const longlong2 h1 = __ldg(reinterpret_cast<const longlong2 *>(tiles + t) + 1);   // {a0 | a1 << 32, flags}
+                if (k == S) {
+                    ring::grid_dep_wait();
+                    if (done_flag && __ldcg(done_flag) != 0.0) break;
+                }
+                if (k >= S) ring::mbar_wait(&empty[s], ((k / S) - 1) & 1);
+                *reinterpret_cast<longlong2 *>(st + Cfg::HDR_OFF) = h0;
+                *reinterpret_cast<longlong2 *>(st + Cfg::HDR_OFF + 16) = h1;
+                const int64_t b0 = h0.x, b1 = h0.y;
+                const int a0 = (int)(h1.x & 0xffffffffll), a1 = (int)(h1.x >> 32);
+                const int64_t i0 = b0 & ~(int64_t)3;
+                const int p0 = a0 & ~1;
+                const uint32_t bytes_v = (uint32_t)(b1 - b0) * 32u;
+                const uint32_t bytes_i = bytes_v ? (((uint32_t)(b1 - i0) * 4u + 15u) & ~15u) : 0u;
+                const uint32_t bytes_p = ((uint32_t)(a1 + 1 - p0) * 8u + 15u) & ~15u;
+                ring::mbar_arrive_tx(&full[s], bytes_v + bytes_i + bytes_p);
+                if (bytes_v) {
+                    if (Cfg::EVICT_FIRST) {
+                        ring::bulk_g2s_hint(st + Cfg::VAL_OFF, data + 4 * b0, bytes_v, &full[s], pol);
+                        ring::bulk_g2s_hint(st + Cfg::IDX_OFF, node_idx + i0, bytes_i, &full[s], pol);
+                    } else {
+                        ring::bulk_g2s(st + Cfg::VAL_OFF, data + 4 * b0, bytes_v, &full[s]);
+                        ring::bulk_g2s(st + Cfg::IDX_OFF, node_idx + i0, bytes_i, &full[s]);
+                    }
+                }
+                ring::bulk_g2s(st + Cfg::PTR_OFF, node_ptr + p0, bytes_p, &full[s]);
+            }
+            // a CTA must not exit with bulk copies in flight: when the consumers leave early (stop flag) nobody waits on the
+            // stages this lane filled, so it does
+            ring::grid_dep_wait();
+            if (done_flag && __ldcg(done_flag) != 0.0) {
+                const int filled = k < S ? k : S;
+                for (int s = 0; s < filled; s++) ring::mbar_wait(&full[s], 0);
             }
         }
-        return;
+        ring::grid_dep_wait();       // the other lanes of the warp: the flag may only be read behind the dependency
+        if (!TRIG_LATE) ring::grid_dep_launch();
+        return !(done_flag && __ldcg(done_flag) != 0.0);
     }
     // ---- consumers
+    ring::grid_dep_wait();       // no-ops unless the kernel was launched with the programmatic-serialization attribute
+    if (!TRIG_LATE) ring::grid_dep_launch();
+    if (done_flag && __ldcg(done_flag) != 0.0) return false;
     const int sub = lane & 7, grp4 = lane >> 3;
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
-    const double2 *r2 = reinterpret_cast<const double2 *>(r), *d2 = reinterpret_cast<const double2 *>(dinv);
     int k = 0;
     for (int t = blockIdx.x; t < n_tile; t += gridDim.x, k++) {
         const int s = k % S;
@@ -216,9 +188,6 @@ __device__ __forceinline__ void ring_main(unsigned char *smem, RingState rs, int
                 off = (int)(r0 - b0);
                 deg = (int)(ps[row - a0 + 1] - r0);
             }
-            // the row's own entries of p, r, D^-1 (for the sums) travel while the row is multiplied
-            double2 pa = make_double2(0.0, 0.0), ra = pa, da = pa;
-            if (valid && sub == 0) { pa = __ldg(x2 + row); ra = r2[row]; da = d2[row]; }
             double y0 = 0.0, y1 = 0.0;
             for (int kb = sub; kb < deg; kb += 32) {
                 double2 v0[4], v1[4], xv[4];
@@ -252,12 +221,15 @@ __device__ __forceinline__ void ring_main(unsigned char *smem, RingState rs, int
                     if (fx.y) y1 = 0.0;
                 }
                 *reinterpret_cast<double2 *>(y + 2 * (int64_t)row) = make_double2(y0, y1);
-                ring_row_dots(dots, pa, ra, da, y0, y1);
+                const double2 xa = __ldg(x2 + row);
+                dot = fma(xa.x, y0, dot); dot = fma(xa.y, y1, dot);
             }
         }
         __syncwarp();
         if (lane == 0) ring::mbar_arrive(&empty[s]);
     }
+    if (TRIG_LATE) ring::grid_dep_launch();
+    return true;
 }
 
 }  // namespace mofem
