@@ -30,6 +30,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 METRIC = "overlay-cell stiffness assembly cells/s (fp64) and K-assembly+solve wall time"
+FAMILY_TEXT = {"quad": "2 meshes, quad4/quad4", "tri": "2 meshes, quad4/tri3", "m3s": "3 meshes, staggered third mesh, quad4: cells with 1/2/3 incident elements"}
 UNIT = "cells/s"
 
 
@@ -114,11 +115,10 @@ def algorithmic_bytes(info, n_dof):
     n_contrib = info["n_coo"] // 4
     return {
         # block CSR as stored: 8 B per value + one 4 B column index per 2x2 block + node_ptr + x, y + fixed mask
-        # + r and dinv of the produced rows (the sums of the single-reduction PCG are taken inside the SpMV)
-        "spmv": 8 * nnz + nnz + 8 * (n_node + 1) + 8 * n_dof + 8 * n_dof + n_dof + 16 * n_dof,
+        "spmv": 8 * nnz + nnz + 8 * (n_node + 1) + 8 * n_dof + 8 * n_dof + n_dof,
         # SURVEY.md section 8d scalar-CSR figure for the same product (12 B per stored entry)
         "spmv_scalar_csr": 12 * nnz + 4 * (n_dof + 1) + 16 * n_dof,
-        "vec": 8 * n_dof * 8,            # k_pcg_vec: reads q, r, dinv, p, x; writes r, x, p
+        "vec": 8 * n_dof * 8,            # k_pcg_vec: reads q, r, dinv, p, x; writes r, x, p (p's second read comes out of L2)
         # numeric reduce: every block value once (32 B per node pair), its 4 B source slot, CSR values out
         "numeric": 32 * n_pair + 4 * n_contrib + 8 * nnz,
     }
@@ -132,6 +132,10 @@ def integration_flops(fp, info, ms):
     87 k + 167 (k Newton updates), per (point, block) contraction 304, regular quad4 element 4 x (95 + 304).
     ``algorithmic`` counts ONE evaluation per (point, incident element) -- the minimum; ``executed`` counts what the
     thread-per-block kernels (like the reference) do: the off-diagonal block re-evaluates both elements."""
+    if not (np.asarray(fp.elem_nn) == 4).all():
+        # the survey's flop model is written for quad4 elements; tri3 patches (closed-form inverse map, 3/4-point rules) only get counts
+        return {"newton_updates_per_evaluation": info["newton_updates"] / max(info["n_eval"], 1), "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+                "note": "flop model of SURVEY.md section 8d covers quad4 cells only"}
     ce = np.asarray(fp.cell_elem)
     m = (ce >= 0).sum(1)
     tri = np.diff(np.asarray(fp.cell_tri_ptr))
@@ -234,7 +238,10 @@ def main():
     ap.add_argument("--l2-persist", type=int, default=0, help="L2 persistence window over the PCG vectors (library default: 0)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange / dot-product reduction over NVLink peer memory inside the kernels, or NCCL calls")
-    ap.add_argument("--meshes", type=int, default=2, choices=[2, 3], help="2: syn-1M family; 3: multi-mesh variant")
+    ap.add_argument("--family", default="quad", choices=["quad", "tri", "m3s"],
+                    help="synthetic overlay family: quad = 2 meshes, quad4 patches (BASELINE config 3 variant a, the headline workload); "
+                         "tri = patch quads split into tri3 (variant b); m3s = staggered third mesh, cells with 1/2/3 incident "
+                         "elements (config 4: --n0 1608 gives ~10 M cells)")
     ap.add_argument("--host-overlay", action="store_true",
                     help="build the overlay with the NumPy generator instead of the CUDA kernels (1 GPU) / their host build (N > 1 strips); "
                          "same bits, untimed either way")
@@ -272,14 +279,19 @@ def main():
     part = None
     n_cells_global = None
     overlay_ms = None
-    if world == 1 and not args.host_overlay:
+    n_meshes = 3 if args.family == "m3s" else 2
+    if world == 1 and args.family != "quad":
+        # general families: clipping per mesh-0 element on the host (csrc/overlay_general.h), pinned against the reference's sweep
+        from mofem_b200.overlay_gen import general_family
+        fp, rhs, fixed, val = general_family(args.n0, args.family)
+    elif world == 1 and not args.host_overlay:
         # overlay by pairwise convex clipping on the GPU (csrc/overlay.cu; bit-identical to the NumPy generator)
         from mofem_b200.overlay_gen import patch_family_gpu
         torch.cuda.set_device(local)
         with Context(local) as gen_ctx:
-            fp, rhs, fixed, val, overlay_ms = patch_family_gpu(gen_ctx, args.n0, n_mesh=args.meshes, to_host=True)
+            fp, rhs, fixed, val, overlay_ms = patch_family_gpu(gen_ctx, args.n0, to_host=True)
     elif world == 1:
-        fp, rhs, fixed, val = patch_family(args.n0, n_mesh=args.meshes)
+        fp, rhs, fixed, val = patch_family(args.n0)
     else:
         from mofem_b200.distributed import init_comm
         from mofem_b200.partition import exchange_send_lists, partition_problem
@@ -291,12 +303,20 @@ def main():
         else:
             ny, per = args.n0 * world, px                  # a stack of N blocks of n0 x n0
         rows_per_rank = 8 * per
-        strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per), n_mesh=args.meshes,
-                                                    engine="numpy" if args.host_overlay else "native")
         n_node0 = (args.n0 + 1) * (ny + 1)
-        owner = np.empty(strip.n_node, np.int32)
-        owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // rows_per_rank, world - 1)
-        owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // px) // per
+        if args.family == "quad":
+            strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per),
+                                                        engine="numpy" if args.host_overlay else "native")
+            owner = np.empty(strip.n_node, np.int32)
+            owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // rows_per_rank, world - 1)
+            owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // px) // per
+            # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
+            own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)      # (one mesh-0 element row per strip boundary)
+        else:
+            # rank r owns the nodes whose nominal row lies in its element rows; it integrates every cell that touches one
+            # of them (the generator emits a margin of 3 element rows, the partitioner keeps what is needed)
+            from mofem_b200.overlay_gen import general_strip
+            strip, rhs_g, fixed_g, val_g, owner, own_cells = general_strip(args.n0, args.family, ny, rank, world)
         # weak scaling keeps the physics per block fixed: every block carries the corner load of the 1-GPU problem on
         # its own bottom-right node (a single load on a domain N times taller would need ~N times more CG iterations
         # just to propagate across the height); strong scaling solves the one problem as it is
@@ -306,8 +326,6 @@ def main():
         part = partition_problem(strip, owner, rank, world)
         fp = part.fp
         rhs, fixed, val = part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g)
-        # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
-        own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)      # (one mesh-0 element row per strip boundary)
         del strip, rhs_g, fixed_g, val_g, owner
 
     torch.cuda.set_device(local)
@@ -439,7 +457,7 @@ def main():
     roofline = None
     traffic = None    # dram__bytes_read + dram__bytes_write per SpMV launch, from the committed ncu capture of this workload
     tpath = os.path.join(REPO, "profiles", "r1_spmv_traffic.json")
-    if world == 1 and args.n0 == 664 and args.meshes == 2 and os.path.exists(tpath):
+    if world == 1 and args.n0 == 664 and args.family == "quad" and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]
     if spmv_ms:
@@ -477,7 +495,7 @@ def main():
         "metric": METRIC, "value": cells_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"syn-{max(1, round(cells_total / (1 if args.strong else world) / 1e6))}M patch-family overlay ({args.meshes} meshes, quad4/quad4, jitter 0.12h): assembly + Jacobi-PCG",
+        "config": {"workload": f"syn-{max(1, round(cells_total / (1 if args.strong else world) / 1e6))}M patch-family overlay ({FAMILY_TEXT[args.family]}, jitter 0.12h): assembly + Jacobi-PCG",
                    "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
                    "nnz": info["nnz"], "rtol_true_residual": args.rtol,
                    "l2": f"inputs larger than L2 (per GPU: CSR {9 * info['nnz'] / 1e9:.2f} GB, block values {32 * info['n_pair'] / 1e9:.2f} GB vs 126 MB L2)",

@@ -45,9 +45,9 @@ HOST_LIB = os.path.join(HERE, "liboverlay_host.so")
 def build_host(force=False, verbose=False):
     """Host build of the overlay core (csrc/overlay_host.cpp): preprocessing without a device + the CPU parity check."""
     src = os.path.join(CSRC, "overlay_host.cpp")
-    hdr = os.path.join(CSRC, "overlay_core.h")
-    if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", HOST_LIB]
+    hdrs = [os.path.join(CSRC, "overlay_core.h"), os.path.join(CSRC, "overlay_general.h")]
+    if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", src, "-o", HOST_LIB]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

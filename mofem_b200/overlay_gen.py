@@ -32,6 +32,7 @@ from .flatten import CELL_OVERLAY, CELL_REGULAR, SOLVER_LOWER, FlatProblem, mate
 PERIOD = 8
 PATCH = 5
 OFF_X, OFF_Y = 1.37, 1.41
+OFF2_X, OFF2_Y = 4.71, 4.19        # staggered third mesh
 SEED = 20260101
 
 
@@ -43,6 +44,7 @@ class PatchMeshes:
     Py: int
     X0: np.ndarray            # [ny+1, nx+1, 2] mesh-0 node coordinates, indexed [j, i]
     X1: np.ndarray            # [Py, Px, 6, 6, 2] mesh-1 node coordinates, indexed [b, a, t, s]
+    X2: np.ndarray = None     # [Py-1, Px-1, 6, 6, 2] staggered mesh-2 patches (family "m3s"), else None
 
     @property
     def n0(self): return self.nx
@@ -74,7 +76,7 @@ class PatchMeshes:
         return (base[:, None, None] + e[None]).reshape(-1, 4)
 
 
-def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED, ny: int = None) -> PatchMeshes:
+def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED, ny: int = None, stagger: bool = False) -> PatchMeshes:
     nx = n0
     ny = nx if ny is None else ny
     if nx % PERIOD or nx < PERIOD or ny % PERIOD or ny < PERIOD:
@@ -94,7 +96,17 @@ def patch_meshes(n0: int, jitter: float = 0.12, seed: int = SEED, ny: int = None
     jit1[:, :, 0, :] = jit1[:, :, 5, :] = 0.0
     jit1[:, :, :, 0] = jit1[:, :, :, 5] = 0.0
     X1 = (X1 + jit1) * h
-    return PatchMeshes(nx=nx, ny=ny, Px=Px, Py=Py, X0=X0, X1=X1)
+    X2 = None
+    if stagger:           # drawn after X0 and X1, so those are the same arrays as without the third mesh
+        if Px < 2 or Py < 2:
+            raise ValueError("the staggered third mesh needs n0 >= 16")
+        b, a, t, s = np.meshgrid(np.arange(Py - 1), np.arange(Px - 1), np.arange(6), np.arange(6), indexing="ij")
+        X2 = np.stack([PERIOD * a + OFF2_X + s, PERIOD * b + OFF2_Y + t], -1).astype(np.float64)
+        jit2 = rng.uniform(-jitter, jitter, X2.shape)
+        jit2[:, :, 0, :] = jit2[:, :, 5, :] = 0.0
+        jit2[:, :, :, 0] = jit2[:, :, :, 5] = 0.0
+        X2 = (X2 + jit2) * h
+    return PatchMeshes(nx=nx, ny=ny, Px=Px, Py=Py, X0=X0, X1=X1, X2=X2)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -535,6 +547,18 @@ def _patch_mesh_ids(Px, Py, n_mesh):
     return (1 + ((a + b) % 2 if n_mesh == 3 else 0 * a)).reshape(-1).astype(np.int32)
 
 
+def family_deck(n0: int, family: str, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3, solver: int = 1):
+    """Reference ``inputData`` tuple of the general families (:func:`general_family`): "m3s" = staggered third mesh
+    (BASELINE config 4), "tri" = patch quads split into 3-node triangles (config 3 variant b)."""
+    gm = general_meshes(n0, family, jitter, seed)
+    coords = gm.node_xy.tolist()
+    meshes = [gm.elem_nodes[gm.elem_mesh == k][:, :gm.nn_of_mesh[k]].tolist() for k in range(gm.n_mesh)]
+    material_mesh = [[0] * len(m) for m in meshes]
+    constraints = [[j * (n0 + 1), 1, 1, 0.0, 0.0] for j in range(n0 + 1)]
+    forces = [[], [[n0, 1.0, -0.5]]]
+    return ([solver, 1], None, None, meshes, material_mesh, coords, [[E, nu]], constraints, [0, 0, 1], forces)
+
+
 def patch_deck(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3, solver: int = 1,
                n_mesh: int = 2):
     """The same problem as a reference ``inputData`` tuple (inputFunctions/inputF.py:204-205, concentrated-force
@@ -548,3 +572,165 @@ def patch_deck(n0: int, jitter: float = 0.12, seed: int = SEED, E: float = 1000.
     constraints = [[j * (n0 + 1), 1, 1, 0.0, 0.0] for j in range(n0 + 1)]
     forces = [[], [[n0, 1.0, -0.5]]]
     return ([solver, 1], None, None, meshes, material_mesh, coords, [[E, nu]], constraints, [0, 0, 1], forces)
+
+
+# ---------------------------------------------------------------------------------------------
+# general families: any number of patch meshes, quad4 or tri3 patch elements (overlay by liboverlay_host.so)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class GeneralMeshes:
+    nx: int
+    ny: int
+    n_mesh: int
+    node_xy: np.ndarray        # [n_node, 2]
+    elem_nodes: np.ndarray     # [n_elem, 9] padded with -1
+    elem_nn: np.ndarray        # [n_elem]
+    elem_mesh: np.ndarray      # [n_elem]
+    nn_of_mesh: list           # nodes per element of every mesh
+    mesh_offset: list          # [n_mesh + 1] first element of every mesh
+    patch: list                # per patch mesh: dict(Px, Py, off_x, off_y, tri, node0, elem0, X [Py, Px, 6, 6, 2])
+
+
+def general_meshes(n0: int, family: str, jitter: float = 0.12, seed: int = SEED, ny: int = None) -> GeneralMeshes:
+    """Meshes of a general family: "tri" (2 meshes, every patch quad split into two 3-node triangles), "m3s" (3 meshes: the
+    disjoint patches of the 2-mesh family + staggered mesh-2 patches at ((8a+4.71)h, (8b+4.19)h), a, b < n0/8 - 1),
+    "quad" (the 2-mesh family itself, for cross-checks against :func:`patch_family`)."""
+    if family not in ("quad", "tri", "m3s"):
+        raise ValueError("family must be 'quad', 'tri' or 'm3s'")
+    pm = patch_meshes(n0, jitter, seed, ny, stagger=(family == "m3s"))
+    nx, ny = pm.nx, pm.ny
+    tri = family == "tri"
+    patch = [dict(Px=pm.Px, Py=pm.Py, off_x=OFF_X, off_y=OFF_Y, tri=tri, X=np.ascontiguousarray(pm.X1))]
+    if family == "m3s":
+        patch.append(dict(Px=pm.Px - 1, Py=pm.Py - 1, off_x=OFF2_X, off_y=OFF2_Y, tri=False, X=np.ascontiguousarray(pm.X2)))
+    node_xy = [pm.X0.reshape(-1, 2)]
+    en = [np.pad(pm.elem_nodes0(), ((0, 0), (0, 5)), constant_values=-1)]
+    nn = [np.full(pm.n_elem0, 4, np.int32)]
+    em = [np.zeros(pm.n_elem0, np.int32)]
+    node0, elem0 = pm.n_node0, pm.n_elem0
+    offs = [0, pm.n_elem0]
+    for k, pt in enumerate(patch):
+        npatch = pt["Px"] * pt["Py"]
+        pt["node0"], pt["elem0"] = node0, elem0
+        node_xy.append(pt["X"].reshape(-1, 2))
+        t, s = np.meshgrid(np.arange(5), np.arange(5), indexing="ij")
+        loc = (6 * t + s).reshape(-1)
+        quad = np.stack([loc, loc + 1, loc + 7, loc + 6], 1)                      # [25, 4] CCW
+        if pt["tri"]:
+            # (q0, q1, q2), (q0, q2, q3) -- except on the anti-diagonal (p + q == 4), where the cut runs q1-q3: with the plain
+            # split the patch corners (5, 0) and (0, 5) belong to one triangle whose three nodes all carry weight 0, rho_1
+            # vanishes on it, the corner node gets no stiffness and the reference's own spsolve reports a singular matrix
+            anti = ((t + s) == 4).reshape(-1)
+            e = np.where(anti[:, None, None], np.stack([quad[:, [0, 1, 3]], quad[:, [1, 2, 3]]], 1),
+                         np.stack([quad[:, [0, 1, 2]], quad[:, [0, 2, 3]]], 1)).reshape(-1, 3)   # [50, 3]
+        else:
+            e = quad
+        base = node0 + 36 * np.arange(npatch)
+        ee = (base[:, None, None] + e[None]).reshape(-1, e.shape[1])
+        en.append(np.pad(ee, ((0, 0), (0, 9 - e.shape[1])), constant_values=-1))
+        nn.append(np.full(len(ee), e.shape[1], np.int32))
+        em.append(np.full(len(ee), k + 1, np.int32))
+        node0 += 36 * npatch
+        elem0 += len(ee)
+        offs.append(elem0)
+    return GeneralMeshes(nx=nx, ny=ny, n_mesh=1 + len(patch), node_xy=np.ascontiguousarray(np.concatenate(node_xy)),
+                         elem_nodes=np.concatenate(en).astype(np.int32), elem_nn=np.concatenate(nn), elem_mesh=np.concatenate(em),
+                         nn_of_mesh=[4] + [3 if pt["tri"] else 4 for pt in patch], mesh_offset=offs, patch=patch)
+
+
+def _general_overlay(gm: GeneralMeshes, j_lo: int, j_hi: int, X0: np.ndarray, threads: int = None):
+    """Cell / triangle arrays of the mesh-0 element rows ``[j_lo, j_hi)`` from liboverlay_host.so (overlay_general.h)."""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboverlay_host.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -m mofem_b200.build`")
+    L = C.CDLL(path)
+    L.ovl_general_build.restype = C.c_void_p
+    L.ovl_general_error.restype = C.c_char_p
+    L.ovl_general_error.argtypes = [C.c_void_p]
+    L.ovl_general_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.ovl_general_copy.argtypes = [C.c_void_p] * 6
+    L.ovl_general_free.argtypes = [C.c_void_p]
+    npm = len(gm.patch)
+    px = np.array([pt["Px"] for pt in gm.patch], np.int32); py = np.array([pt["Py"] for pt in gm.patch], np.int32)
+    tri = np.array([int(pt["tri"]) for pt in gm.patch], np.int32)
+    e0 = np.array([pt["elem0"] for pt in gm.patch], np.int64)
+    Xs = (C.c_void_p * npm)(*[pt["X"].ctypes.data for pt in gm.patch])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if threads is None:
+        threads = int(os.environ.get("MOFEM_GEN_WORKERS", max(1, min(16, (os.cpu_count() or 1)))))
+    X0 = np.ascontiguousarray(X0)
+    h = L.ovl_general_build(C.c_int(gm.nx), C.c_int(gm.ny), C.c_int(j_lo), C.c_int(j_hi), p(X0), C.c_int(npm), p(px), p(py), p(tri),
+                            p(e0), Xs, C.c_int(threads))
+    try:
+        err = L.ovl_general_error(h)
+        if err:
+            raise RuntimeError("overlay: " + err.decode())
+        sz = np.zeros(2, np.int64)
+        L.ovl_general_sizes(h, p(sz))
+        n_cell, n_tri = int(sz[0]), int(sz[1])
+        out = dict(cell_elem=np.empty((n_cell, gm.n_mesh), np.int32), cell_kind=np.empty(n_cell, np.int32),
+                   cell_tri_ptr=np.empty(n_cell + 1, np.int64), tri_xy=np.empty((n_tri, 3, 2)), tri_rho=np.empty((n_tri, 3, gm.n_mesh)))
+        L.ovl_general_copy(h, p(out["cell_elem"]), p(out["cell_kind"]), p(out["cell_tri_ptr"]), p(out["tri_xy"]), p(out["tri_rho"]))
+    finally:
+        L.ovl_general_free(h)
+    return out
+
+
+def general_family(n0: int, family: str, jitter: float = 0.12, seed: int = SEED, E: float = 1000.0, nu: float = 0.3,
+                   solver: int = SOLVER_LOWER, ny: int = None, elem_rows=None, threads: int = None):
+    """Flattened problem of a general family + its linear system, like :func:`patch_family`:
+
+    * ``"tri"``  -- BASELINE config 3 variant b: the 2-mesh family with every patch quad split into two 3-node triangles
+      (quad4 x tri3 cells: closed-form ``invTri``, the 4-point rule of ``n1 + n2 = 7``);
+    * ``"m3s"``  -- BASELINE config 4: a third mesh of staggered patches at ``((8a+4.71)h, (8b+4.19)h)`` that overlaps
+      mesh 0 everywhere and the mesh-1 patches partially: cells with 1, 2 and 3 incident elements, every ``l > j`` block of
+      ``AMORE.py:100-123``;
+    * ``"quad"`` -- the 2-mesh family again (cross-check against :func:`patch_family`).
+
+    The overlay comes from ``liboverlay_host.so`` (``csrc/overlay_general.h``: clipping per mesh-0 element), pinned against
+    the reference's plane sweep by the ``patch16_tri`` / ``patch16_m3s`` / ``patch32_m3s`` fixtures.
+    ``elem_rows=(j_lo, j_hi)`` emits only the cells of those mesh-0 element rows (strips for the row-partitioned solve)."""
+    gm = general_meshes(n0, family, jitter, seed, ny)
+    nx, ny = gm.nx, gm.ny
+    j_lo, j_hi = (0, ny) if elem_rows is None else (int(elem_rows[0]), int(elem_rows[1]))
+    if not (0 <= j_lo < j_hi <= ny):
+        raise ValueError("elem_rows out of range")
+    n_node0 = (nx + 1) * (ny + 1)
+    cells = _general_overlay(gm, j_lo, j_hi, gm.node_xy[:n_node0].reshape(ny + 1, nx + 1, 2), threads)
+    fp = FlatProblem(
+        solver=int(solver), n_mesh=gm.n_mesh, node_xy=gm.node_xy, elem_nodes=gm.elem_nodes, elem_nn=gm.elem_nn,
+        elem_mat=np.zeros(len(gm.elem_nn), np.int32), elem_mesh=gm.elem_mesh, mat_D=material_matrix([E, nu], 1).reshape(1, 3, 3),
+        n_mesh_regular=0, mesh_offset=list(gm.mesh_offset), **cells)
+    n_dof = 2 * len(gm.node_xy)
+    fixed = np.zeros(n_dof, dtype=np.uint8)
+    left = np.arange(ny + 1) * (nx + 1)
+    fixed[2 * left] = 1; fixed[2 * left + 1] = 1
+    rhs = np.zeros(n_dof)
+    rhs[2 * nx] = 1.0; rhs[2 * nx + 1] = -0.5
+    return fp, rhs, fixed, np.zeros(n_dof)
+
+
+def general_strip(n0: int, family: str, ny: int, rank: int, world: int, jitter: float = 0.12, seed: int = SEED, threads: int = None):
+    """What rank ``rank`` of ``world`` needs from a general family on an ``n0 x ny`` domain cut into ``world`` strips of equal
+    height (``ny / world`` element rows, a multiple of 8): the cells of its element rows plus a margin of 3 rows (a superset
+    of every cell that touches a node it owns -- :func:`mofem_b200.partition.partition_problem` keeps what is needed), the
+    node owner array (a node belongs to the strip its nominal row lies in), and the number of cells in exactly its rows.
+    Returns ``(FlatProblem, rhs, fixed, fixed_value, owner, own_cells)``; node and element ids are global."""
+    if ny % world or (ny // world) % PERIOD:
+        raise ValueError("ny / world must be a multiple of 8")
+    rows_per_rank = ny // world
+    j_lo, j_hi = rank * rows_per_rank, (rank + 1) * rows_per_rank
+    strip, rhs, fixed, val = general_family(n0, family, jitter, seed, ny=ny, elem_rows=(max(j_lo - 3, 0), min(j_hi + 3, ny)), threads=threads)
+    gm = general_meshes(n0, family, jitter, seed, ny)
+    n_node0 = (n0 + 1) * (ny + 1)
+    owner = np.empty(strip.n_node, np.int32)
+    owner[:n_node0] = np.minimum((np.arange(n_node0) // (n0 + 1)) // rows_per_rank, world - 1)
+    for pt in gm.patch:
+        b, a, t, s_ = np.meshgrid(np.arange(pt["Py"]), np.arange(pt["Px"]), np.arange(6), np.arange(6), indexing="ij")
+        row = np.floor(PERIOD * b + pt["off_y"] + t).astype(np.int64).reshape(-1)
+        owner[pt["node0"]:pt["node0"] + row.size] = np.minimum(row // rows_per_rank, world - 1)
+    erow = strip.cell_elem[:, 0] // n0
+    own_cells = int(((erow >= j_lo) & (erow < j_hi)).sum())
+    return strip, rhs, fixed, val, owner, own_cells

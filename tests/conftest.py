@@ -11,7 +11,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
-FIXTURES = ("simpleOFE3", "AMOREBracket", "patch16", "patch16_m3", "single_lower", "single_icm", "single_quad", "zoo_s1", "zoo_s2", "zoo_s3")
+FIXTURES = ("simpleOFE3", "AMOREBracket", "patch16", "patch16_m3", "patch16_tri", "patch16_m3s", "single_lower", "single_icm", "single_quad", "zoo_s1", "zoo_s2", "zoo_s3")
 
 
 def pytest_configure(config):

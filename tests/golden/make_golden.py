@@ -373,6 +373,22 @@ def newton_vectors(seed=11):
     return out
 
 
+def general_families(names=("patch16_tri", "patch16_m3s", "patch32_m3s")):
+    """The general families of mofem_b200/overlay_gen.py (BASELINE config 3 variant b: patch quads split into tri3;
+    config 4: staggered third mesh, cells with 1, 2 and 3 incident elements) through the reference's own plane sweep.
+    The graph dump (only needed by the drop-in tests of the shipped problems) is left out to keep the files small."""
+    from mofem_b200 import overlay_gen
+    planeSweepMeshes.scale = [1, 1]
+    for name in names:
+        n0 = int(name[5:7]); fam = name.split("_")[1]
+        d, _ = run_amore(name, overlay_gen.family_deck(n0, fam))
+        d.pop("graph", None)
+        if n0 > 16:      # the larger fixture pins counts, pattern and values; triplet lists stay out of the repo
+            for k in ("coo_I", "coo_J", "coo_V", "red_indptr", "red_indices", "red_data", "red_x"):
+                d.pop(k, None)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     for stem in ("simpleOFE3", "AMOREBracket"):
@@ -385,6 +401,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "patch16.npz"), **d)
     d, _ = run_amore("patch16_m3", overlay_gen.patch_deck(16, n_mesh=3))     # three meshes (patches alternate)
     np.savez_compressed(os.path.join(HERE, "patch16_m3.npz"), **d)
+    general_families()
     # the reference's shipped golden output (solution.txt, AMOREBracket, solver 3) as numbers
     from mofem_b200 import solution_io
     disp, energy, name = solution_io.read_solution(os.path.join(REF, "solution.txt"))

@@ -1,6 +1,8 @@
-"""Size-independent properties at the bench workload's full size (syn-1M: n0 = 664, 1.02 M overlay cells, 1.38 M DOF):
-where the oracle cannot finish in seconds, the CUDA path is checked through invariants of the discretisation, plus a
-random subsample of cells against the oracle."""
+"""Size-independent properties at the bench workload's full size (syn-1M: n0 = 664, 1.02 M overlay cells, 1.38 M DOF) for the
+three synthetic families -- "quad" (BASELINE config 3 variant a), "tri" (variant b: tri3 patches, 1.54 M cells) and "m3s"
+(config 4's family: staggered third mesh, 1.71 M cells with 1, 2 and 3 incident elements): where the oracle cannot finish in
+seconds, the CUDA path is checked through invariants of the discretisation, plus a random subsample of cells against the
+oracle."""
 import numpy as np
 import pytest
 
@@ -9,18 +11,30 @@ pytestmark = pytest.mark.gpu
 N0 = 664
 
 
-@pytest.fixture(scope="module")
-def big(gpu_ctx):
+@pytest.fixture(scope="module", params=["quad", "tri", "m3s"])
+def big(gpu_ctx, request):
     from mofem_b200 import overlay_gen
-    fp, rhs, fixed, val = overlay_gen.patch_family(N0, engine="native")   # no forked workers inside a process that holds a CUDA context
+    if request.param == "quad":
+        fp, rhs, fixed, val = overlay_gen.patch_family(N0, engine="native")   # no forked workers inside a process that holds a CUDA context
+    else:
+        fp, rhs, fixed, val = overlay_gen.general_family(N0, request.param)
     gpu_ctx.clear_halo()
     gpu_ctx.set_problem(fp).symbolic().assemble()
+    fp.family = request.param
     return fp, rhs, fixed, val
 
 
 def test_sizes_match_the_survey(big, gpu_ctx):
     fp, *_ = big
     info = gpu_ctx.info()
+    if fp.family == "tri":      # same nodes as the quad family, twice the patch elements
+        assert fp.n_dof == 2 * (665 ** 2 + 6889 * 36) and fp.elem_nn[664 ** 2:].tolist() == [3] * (6889 * 50)
+        assert (fp.cell_elem[:, 1] >= 0).sum() > 1.2e6
+        return
+    if fp.family == "m3s":      # cells with 1, 2 and 3 incident elements
+        m = (fp.cell_elem >= 0).sum(1)[fp.cell_kind == 1]
+        assert fp.n_mesh == 3 and np.bincount(m)[1:].min() > 2e5 and 1.6e6 < fp.n_cell < 1.8e6
+        return
     assert fp.n_dof == 2 * (665 ** 2 + 6889 * 36) == info["n_dof"]
     # per patch period 28672 COO triplets, of which 28 untouched quadFE cells * 64
     assert 0.99e6 < fp.n_cell < 1.03e6 and info["n_coo"] == 28672 * 6889 + 64 * (664 ** 2 - 64 * 6889)
@@ -45,8 +59,13 @@ def test_symmetry_and_rigid_body_null_space(big, gpu_ctx):
     tx = np.zeros(fp.n_dof); tx[0::2] = 1.0
     ty = np.zeros(fp.n_dof); ty[1::2] = 1.0
     rot = np.empty(fp.n_dof); rot[0::2] = -fp.node_xy[:, 1]; rot[1::2] = fp.node_xy[:, 0]
-    for mode in (tx, ty, rot):        # partition of unity + isoparametric completeness: K annihilates rigid motions
-        assert np.abs(gpu_ctx.spmv(mode)).max() <= 1e-9 * scale
+    # partition of unity + isoparametric completeness: K annihilates rigid motions -- exactly, when every block of a cell uses the
+    # same quadrature rule (quad4 x quad4: 6 points throughout).  In a quad4 x tri3 cell the reference integrates the three
+    # blocks with 6, 4 and 3 points (stiffnessMatrix.py:104-106, nInt from n1 + n2), so the cancellation between the blocks of a
+    # row holds only to quadrature accuracy: 5e-5 of the row scale with the reference's own arithmetic (oracle, n0 = 128).
+    tol = 1e-3 if fp.family == "tri" else 1e-9
+    for mode in (tx, ty, rot):
+        assert np.abs(gpu_ctx.spmv(mode)).max() <= tol * scale
 
 
 def test_linear_field_gives_constant_strain_energy(big, gpu_ctx):
@@ -87,7 +106,7 @@ def test_random_cell_subsample_against_the_oracle(big, gpu_ctx):
 def test_solve_energy_identity(big, gpu_ctx):
     fp, rhs, fixed, val = big
     gpu_ctx.set_system(rhs, fixed, val)
-    u, info = gpu_ctx.solve(rtol=1e-10)
+    u, info = gpu_ctx.solve(rtol=1e-10, maxit=400000)
     assert info["converged"] == 1 and info["relres_true"] <= 1e-10
     e = gpu_ctx.energy()
     assert abs(e - 0.5 * rhs @ u) <= 1e-7 * e          # homogeneous Dirichlet data: 1/2 u^T K u = 1/2 f^T u at the solution

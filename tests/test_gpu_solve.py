@@ -23,7 +23,8 @@ def _full_rhs(d, fixed, val, n):
     return f
 
 
-@pytest.mark.parametrize("name", ["simpleOFE3", "AMOREBracket", "single_lower", "single_icm", "single_quad"])
+@pytest.mark.parametrize("name", ["simpleOFE3", "AMOREBracket", "single_lower", "single_icm", "single_quad", "patch16", "patch16_tri",
+                                  "patch16_m3s"])
 def test_displacement_and_energy_match_reference(gpu_ctx, name):
     fp, d = load_golden(name)
     n = fp.n_dof

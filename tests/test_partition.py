@@ -63,6 +63,35 @@ def test_local_rows_are_complete_without_exchange():
     assert seen.all()
 
 
+@pytest.mark.parametrize("family", ["m3s", "tri"])
+def test_general_family_strips_give_complete_rows(family):
+    """Strips of the general families (staggered mesh-2 patches straddle the strip boundary): every rank's local matrix has
+    the complete rows of the nodes it owns, and the owned sets tile the node set."""
+    from oracle import oracle
+    world = 2
+    fp, rhs, fixed, val = overlay_gen.general_family(NX, family, ny=NY)
+    I, J, V, _, _ = oracle.assemble_coo(fp)
+    n = fp.n_dof
+    K = sp.coo_matrix((V, (I, J)), shape=(n, n)).tocsr()
+    x = np.random.default_rng(1).standard_normal(n)
+    y = K @ x
+    seen = np.zeros(fp.n_node, bool)
+    cells = 0
+    for r in range(world):
+        strip, _, _, _, owner, own_cells = overlay_gen.general_strip(NX, family, NY, r, world)
+        cells += own_cells
+        part = partition_problem(strip, owner, r, world)
+        Il, Jl, Vl, _, _ = oracle.assemble_coo(part.fp)
+        nl = part.fp.n_dof
+        Kl = sp.coo_matrix((Vl, (Il, Jl)), shape=(nl, nl)).tocsr()
+        yl = (Kl @ part.local_vector(x))[:2 * part.n_owned_node]
+        own = part.local2global[:part.n_owned_node]
+        assert not seen[own].any()
+        seen[own] = True
+        assert np.abs(yl - y.reshape(-1, 2)[own].reshape(-1)).max() <= 1e-13 * np.abs(y).max()
+    assert seen.all() and cells == fp.n_cell
+
+
 def test_strip_generation_matches_partition_of_the_full_problem():
     fp, *_ = overlay_gen.patch_family(NX, ny=NY)
     owner = _owner(fp, WORLD)
