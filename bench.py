@@ -157,53 +157,74 @@ def integration_flops(fp, info, ms):
             "evaluations_model": evals_done}
 
 
-def run_reference(args):
-    """The reference's CPU algorithm (oracle port, all host threads) + scipy coo->csr + spsolve, on a bounded sample."""
+RUNNER = os.path.join(REPO, "baseline", "ref_runner.py")
+REF_TREE = os.path.join(REPO, "baseline", "_ref", "MOFEM")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_staged():
+    return os.path.isdir(REF_TREE)
+
+
+def run_runner(*argv, timeout=1800):
+    """baseline/ref_runner.py in a subprocess (the unmodified reference staged under baseline/_ref/MOFEM); BLAS pools pinned to
+    one thread so that ``cores`` counts processes (the reference's 2x2 ... 18x18 LAPACK calls do not thread anyway)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, RUNNER] + [str(a) for a in argv], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_runner {argv} failed: {r.stderr[-2000:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def write_cell_sample(fp, n_cells, path, seed=20260101):
+    """A seeded random subsample of the workload's overlay cells as a compact flattened problem (only the elements and nodes the
+    sampled cells touch), for the reference's element functions (ref_runner.py sample)."""
+    rng = np.random.default_rng(seed)
+    n_cells = min(int(n_cells), fp.n_cell)
+    cells = np.sort(rng.choice(fp.n_cell, n_cells, replace=False))
+    tp = np.asarray(fp.cell_tri_ptr)
+    cnt = tp[cells + 1] - tp[cells]
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    sel = np.repeat(tp[cells] - ptr[:-1], cnt) + np.arange(ptr[-1])
+    ce = np.asarray(fp.cell_elem)[cells]
+    elems, inv = np.unique(ce[ce >= 0], return_inverse=True)
+    ce2 = np.full_like(ce, -1); ce2[ce >= 0] = inv
+    en = np.asarray(fp.elem_nodes)[elems]
+    nodes, ninv = np.unique(en[en >= 0], return_inverse=True)
+    en2 = np.full_like(en, -1); en2[en >= 0] = ninv
+    np.savez(path, meta=np.array([fp.solver, fp.n_mesh]), node_xy=np.asarray(fp.node_xy)[nodes], elem_nodes=en2,
+             elem_nn=np.asarray(fp.elem_nn)[elems], elem_mat=np.asarray(fp.elem_mat)[elems], mat_D=np.asarray(fp.mat_D).reshape(-1, 3, 3),
+             cell_elem=ce2, cell_kind=np.asarray(fp.cell_kind)[cells], cell_tri_ptr=ptr, tri_xy=np.asarray(fp.tri_xy)[sel],
+             tri_rho=np.asarray(fp.tri_rho)[sel])
+    return n_cells
+
+
+def workload_text(cells, family):
+    return f"syn-{max(1, round(cells / 1e6))}M patch-family overlay ({FAMILY_TEXT[family]}, jitter 0.12h): assembly + Jacobi-PCG"
+
+
+def family_problem(n0, family, ny=None):
+    from mofem_b200.overlay_gen import general_family, patch_family
+    if family == "quad":
+        return patch_family(n0, ny=ny, engine="native")
+    return general_family(n0, family, ny=ny)
+
+
+def port_figure(n0, cores):
+    """The oracle C port on all host threads + scipy coo->csr + spsolve on a complete small member of the family (the round-1 CPU
+    figure, kept as a second, labelled number)."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     from mofem_b200.overlay_gen import patch_family
     from oracle import oracle
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    n0 = args.ref_n0
-    fp, rhs, fixed, val = patch_family(n0)
-    free = fixed == 0
-
-    def step():
-        I, J, V, _, _ = oracle.assemble_coo(fp, cores)
-        K = sp.coo_matrix((V, (I, J)), shape=(fp.n_dof,) * 2).tocsr()
-        b = (rhs - K @ val)[free]
-        Kff = K[free][:, free].tocsc()
-        x = spla.spsolve(Kff, b)
-        u = val.copy(); u[free] = x
-        return 0.5 * u @ (K @ u)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    v = fp.n_cell / dt
-    sample = (f"patch family n0={n0} ({fp.n_cell} cells, {fp.n_dof} DOF): oracle C port of the reference's assembly "
-              f"on {cores} threads + scipy coo->csr + constraint elimination + spsolve (the reference's own solver)")
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "syn-1M patch-family overlay (2 meshes, quad4/quad4), bounded sample", "n0": n0,
-                      "cells": fp.n_cell, "dof": fp.n_dof},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit(out)
-
-
-def cpu_baseline(n0, budget_cells=None):
-    import scipy.sparse as sp
-    import scipy.sparse.linalg as spla
-    from mofem_b200.overlay_gen import patch_family
-    from oracle import oracle
-    cores = os.cpu_count() or 1
     fp, rhs, fixed, val = patch_family(n0)
     free = fixed == 0
     t0 = time.perf_counter()
@@ -212,13 +233,334 @@ def cpu_baseline(n0, budget_cells=None):
     K = sp.coo_matrix((V, (I, J)), shape=(fp.n_dof,) * 2).tocsr()
     t2 = time.perf_counter()
     b = (rhs - K @ val)[free]
-    x = spla.spsolve(K[free][:, free].tocsc(), b)
+    spla.spsolve(K[free][:, free].tocsc(), b)
     t3 = time.perf_counter()
-    return {"value": fp.n_cell / (t3 - t0), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"patch family n0={n0}: {fp.n_cell} cells, {fp.n_dof} DOF (same family as the workload)",
-            "assembly_cells_per_s": fp.n_cell / (t1 - t0), "coo_to_csr_s": t2 - t1, "spsolve_s": t3 - t2,
-            "note": "oracle = C port of the reference's NumPy arithmetic; the reference's own Python runs at "
-                    "~120-340 cells/s on one thread (BASELINE.md)"}
+    return {"kind": "port", "cores": cores, "value": fp.n_cell / (t3 - t0), "unit": UNIT,
+            "sample": f"complete patch-family problem n0={n0}: {fp.n_cell} cells, {fp.n_dof} DOF; oracle C port of the reference's "
+                      f"assembly on {cores} threads + scipy coo->csr + spsolve",
+            "assembly_cells_per_s": fp.n_cell / (t1 - t0), "coo_to_csr_s": t2 - t1, "spsolve_s": t3 - t2}
+
+
+def cpu_baseline(fp, args):
+    """The CPU figures next to the GPU line (rank 0, N = 1).  Primary: the UNMODIFIED reference (baseline/_ref/MOFEM) -- its
+    element functions stiffnessMatrix.lowerOrderAMORE / quadFE / ... over a seeded subsample of THIS workload's cells, following the
+    cell loop of AMORE.py:59-123, one process (the reference has no parallelism); then the same on all host cores by forking over
+    cells (cells are independent).  The reference's spsolve cannot factor the full system in the budget (1.38 M equations): the
+    figure is assembly only, which favours the CPU side.  Secondary: the round-1 number (oracle C port + scipy + spsolve)."""
+    import tempfile
+    cores = host_cores()
+    out = None
+    if reference_staged():
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "sample.npz")
+            n1 = write_cell_sample(fp, args.ref_cells_1core, path)
+            r1 = run_runner("sample", path, 1)
+            nall = write_cell_sample(fp, args.ref_cells, path)
+            rall = run_runner("sample", path, cores)
+        out = {"value": r1["cells_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"{n1} of the workload's {fp.n_cell} overlay cells (seeded random subsample), integrated by the unmodified reference's "
+                         f"stiffnessMatrix.* + sparsifyElementMatrix in the order of AMORE.py:59-123, one Python process: {r1['wall_s']:.1f} s; "
+                         "assembly only (coo->csr and spsolve of the full 1.38 M-equation system are not run: the direct solver does not fit "
+                         "the time budget), so the figure favours the CPU side",
+               "coo_triplets_sampled": r1["coo_triplets"],
+               "all_cores": {"value": rall["cells_per_s"], "unit": UNIT, "cores": rall["processes"], "kind": "reference",
+                             "sample": f"{nall} cells of the same subsample family forked over {rall['processes']} processes: {rall['wall_s']:.1f} s"}}
+    if not args.no_port_figure:
+        port = port_figure(args.ref_n0, cores)
+        if out is None:
+            out = dict(port, note="baseline/_ref/MOFEM not staged on this box: oracle port only")
+        else:
+            out["port"] = port
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, on the GPU arm's config.  One step =
+    a bounded sample of the workload (args.ref_cells of its overlay cells) integrated by the UNMODIFIED reference's element functions
+    (baseline/_ref/MOFEM), forked over all host cores; value = sampled cells / wall time.  The linear solve is not part of the
+    step: spsolve on the full 1.38 M-equation system does not fit the budget ("n/a"), which favours this arm.  Without the staged
+    reference (it cannot be staged outside the build container) the oracle C port runs the same sample."""
+    import tempfile
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    # N > 1: the GPU arm's problem is a stack of N blocks (weak scaling) or the one block cut into strips (--strong)
+    fp, rhs, fixed, val = family_problem(args.n0, args.family, ny=None if (args.strong or args.gpus == 1) else args.n0 * args.gpus)
+    walls = []
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sample.npz")
+        n = write_cell_sample(fp, args.ref_cells, path)
+        if reference_staged():
+            kind = "reference"
+            for k in range(args.warmup + args.steps):
+                r = run_runner("sample", path, cores)
+                if k >= args.warmup:
+                    walls.append(r["wall_s"])
+            how = (f"unmodified reference (baseline/_ref/MOFEM): stiffnessMatrix.* + sparsifyElementMatrix over the cell loop of "
+                   f"AMORE.py:59-123, forked over {r['processes']} processes")
+        else:
+            kind = "port"
+            from mofem_b200.flatten import FlatProblem
+            from oracle import oracle
+            d = dict(np.load(path))
+            sub = FlatProblem(solver=fp.solver, n_mesh=fp.n_mesh, node_xy=d["node_xy"], elem_nodes=d["elem_nodes"], elem_nn=d["elem_nn"],
+                              elem_mat=d["elem_mat"], elem_mesh=np.zeros(len(d["elem_nn"]), np.int32), mat_D=d["mat_D"], cell_elem=d["cell_elem"],
+                              cell_kind=d["cell_kind"], cell_tri_ptr=d["cell_tri_ptr"], tri_xy=d["tri_xy"], tri_rho=d["tri_rho"])
+            for k in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                oracle.assemble_coo(sub, cores)
+                if k >= args.warmup:
+                    walls.append(time.perf_counter() - t0)
+            how = f"baseline/_ref/MOFEM not staged on this box: oracle C port of the same functions on {cores} threads"
+    dt = sum(walls) / len(walls)
+    v = n / dt
+    sample = (f"{n} of the workload's {fp.n_cell} overlay cells (seeded random subsample) per step; {how}; assembly only -- coo->csr + "
+              "spsolve of the full system: n/a (direct solver does not fit the budget), which favours this arm")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if (args.strong and args.gpus > 1) else "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_text(fp.n_cell / (1 if args.strong else args.gpus), args.family), "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri,
+                      "dof": fp.n_dof, "cells_global": fp.n_cell, "sampled_cells_per_step": n},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    emit(out)
+
+
+SHIPPED = {"bracket": ("AMOREBracket", "AMOREBracket plane-stress bracket with hole (inputFiles/AMOREBracket.txt, solver 3: quadraticICMAMORE), BASELINE configs[1]"),
+           "ofe3": ("simpleOFE3", "simpleOFE3 patch test (3 overlapping meshes, inputFiles/simpleOFE3.txt, solver 2: quadraticAMORE), BASELINE configs[0]")}
+
+
+def run_shipped(args):
+    """--config bracket | ofe3: the reference's two shipped problems (BASELINE configs 2 / 1), 1 GPU.
+    value  : cells / step, step = symbolic + integrate + numeric + constraints + PCG + energy on the flattened problem resident in HBM
+             (the committed fixture of the reference's own flattened overlay, tests/golden/<stem>.npz), CUDA events;
+    e2e    : cells / wall time of the reference-facing ENTRY POINT (mofem_b200.solvers.quadraticICMAMORE / quadraticAMORE) called with
+             the reference's own inputData / overlappingMesh / polygons from its parser and plane sweep -- Python flattening of the
+             object graph, host->device copies, kernels, device->host copy, force vector and constraint glue all inside;
+    cpu_baseline : the UNMODIFIED reference's entry point on the same objects, timed in full, one thread, with its four phase times
+                   (AMORE.py:829,1052,1099,1112)."""
+    import torch
+    from mofem_b200.device import Context
+    from mofem_b200.flatten import FlatProblem
+    stem, text = SHIPPED[args.config]
+    d = dict(np.load(os.path.join(REPO, "tests", "golden", stem + ".npz"), allow_pickle=True))
+    fp = FlatProblem.from_npz_dict(d)
+    fixed = np.zeros(fp.n_dof, np.uint8); val = np.zeros(fp.n_dof)
+    for c in d["constraints"]:
+        nd = int(c[0])
+        if c[1]: fixed[2 * nd] = 1; val[2 * nd] = c[3]
+        if c[2]: fixed[2 * nd + 1] = 1; val[2 * nd + 1] = c[4]
+    free = fixed == 0
+    rhs = np.zeros(fp.n_dof); rhs[free] = d["red_rhs"].reshape(-1)       # fixed values are zero in both decks: f_free = reduced rhs
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (mofem_b200 has no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    ctx = Context(0)
+    ctx.set_profile(0 if args.no_profile else 1)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    keys = [k for k in FlatProblem.ARRAYS if getattr(fp, k) is not None and k != "elem_mesh"]
+    import copy
+    fp_dev = copy.copy(fp)
+    for k in keys:
+        setattr(fp_dev, k, torch.from_numpy(np.ascontiguousarray(getattr(fp, k))).to(dev))
+    rhs_d, fixed_d, val_d = (torch.from_numpy(a).to(dev) for a in (rhs, fixed, val))
+    u_d = torch.empty(fp.n_dof, dtype=torch.float64, device=dev)
+    last = {}
+
+    def step():
+        ctx.set_problem(fp_dev).symbolic().assemble()
+        ctx.set_system(rhs_d, fixed_d, val_d)
+        _, last["solve"] = ctx.solve(rtol=1e-12, maxit=200000, out=u_d)
+        last["energy"] = ctx.energy()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    phases = {"symbolic_ms": 0.0, "integrate_ms": 0.0, "numeric_ms": 0.0, "solve_ms": 0.0}
+    prof = {"spmv_ms": 0.0, "vec_ms": 0.0, "iterations": 0}
+    launches = 0
+    steps = max(args.steps, 20)          # a step is tens of milliseconds: enough of them for the clock sampler to see load
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+        tm = ctx.timing()
+        for k in phases:
+            phases[k] += tm[k]
+        launches += sum(tm["launches"].values()) + 2
+        pp = ctx.pcg_profile()
+        for k in prof:
+            prof[k] += pp[k]
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = ev0.elapsed_time(ev1) / steps
+    info = ctx.info()
+    si = last["solve"]
+    u_fix = u_d.cpu().numpy()
+    n_cells = int((np.asarray(fp.cell_kind) >= 0).sum()) - fp.n_mesh_regular
+    n_regular = fp.n_mesh_regular
+    ctx.close()
+
+    parity = {"fixture_max_rel_du": float(np.abs(u_fix - d["displacement"].reshape(-1)).max() / np.abs(d["displacement"]).max()),
+              "fixture_energy_rel": float(abs(last["energy"] - float(d["energy"].reshape(-1)[0])) / abs(float(d["energy"].reshape(-1)[0])))}
+    e2e = cpu = None
+    if reference_staged():
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            rep = 5
+            g = run_runner("entry", stem, "b200", os.path.join(td, "gpu.npz"), rep)
+            r = run_runner("entry", stem, "ref", os.path.join(td, "ref.npz"), 1)
+            ug, ur = np.load(os.path.join(td, "gpu.npz")), np.load(os.path.join(td, "ref.npz"))
+        runs = g["runs"][2:]                 # the first calls create the context and warm the memory pool
+        entry_s = sum(x["entry_s"] for x in runs) / len(runs)
+        h2d = sum(np.asarray(getattr(fp, k)).nbytes for k in keys) + rhs.nbytes + fixed.nbytes + val.nbytes
+        e2e = {"value": n_cells / entry_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(8 * fp.n_dof + 8),
+               "ms_per_step": entry_s * 1e3,
+               "what": f"mofem_b200.solvers entry point on the reference's own objects (parser + plane sweep of baseline/_ref/MOFEM, untimed: "
+                       f"{g['overlay_s']:.2f} s); mean of {len(runs)} calls after 2 warm-ups",
+               "phases_s": {k: sum(x.get(k, 0.0) for x in runs) / len(runs) for k in ("assembly_s", "force_s", "constraints_s", "solve_s")},
+               "device_ms": {k: sum(x["device_ms"][k] for x in runs) / len(runs) for k in runs[0]["device_ms"]}}
+        rr = r["runs"][0]
+        cpu = {"value": r["cells"] / rr["entry_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"the whole problem, in full: unmodified reference entry point ({'AMORE.quadraticICMAMORE' if stem == 'AMOREBracket' else 'AMORE.quadraticAMORE'}) "
+                         f"on the same objects, one thread: {rr['entry_s']:.2f} s",
+               "phases_s": {k: rr.get(k) for k in ("assembly_s", "force_s", "constraints_s", "solve_s")},
+               "preprocessing_s": {"parser": r["input_s"], "plane_sweep_rho_triangulation": r["overlay_s"]}}
+        du = np.abs(ug["displacement"] - ur["displacement"]).max() / np.abs(ur["displacement"]).max()
+        parity.update({"entry_max_rel_du_vs_reference": float(du),
+                       "entry_energy_rel_vs_reference": float(abs(ug["energy"][0] - ur["energy"][0]) / abs(ur["energy"][0])),
+                       "tolerance": 1e-9})
+        assert du <= 1e-9, f"drop-in displacement differs from the live reference: {du}"
+    else:
+        log("baseline/_ref/MOFEM not staged: no entry-point e2e / reference timing on this box")
+        h_t0 = time.perf_counter()
+        with Context(0) as c2:
+            for _ in range(3):
+                c2.assemble_solve(fp, rhs, fixed, val, rtol=1e-12, maxit=200000)
+            h_t0 = time.perf_counter()
+            for _ in range(5):
+                c2.assemble_solve(fp, rhs, fixed, val, rtol=1e-12, maxit=200000)
+            es = (time.perf_counter() - h_t0) / 5
+        e2e = {"value": n_cells / es, "unit": UNIT, "h2d_bytes_per_step": int(sum(np.asarray(getattr(fp, k)).nbytes for k in keys)),
+               "d2h_bytes_per_step": int(8 * fp.n_dof + 8), "ms_per_step": es * 1e3,
+               "what": "Context.assemble_solve with host buffers (reference not staged on this box: entry-point timing unavailable)"}
+
+    peaks, peak_src = measured_peaks()
+    ab = algorithmic_bytes(info, fp.n_dof)
+    roofline = None
+    if prof["iterations"]:
+        ms = prof["spmv_ms"] / prof["iterations"]
+        ach = ab["spmv"] / (ms * 1e-3) / 1e9
+        roofline = {"kernel": "block-CSR SpMV of the Jacobi-PCG loop", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                    "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "algorithmic_bytes_per_launch": ab["spmv"], "avg_launch_ms": ms,
+                    "note": f"a {info['nnz']}-entry matrix ({ab['spmv'] / 1e6:.2f} MB) lives in L2 and a launch is latency-bound: the HBM "
+                            "roofline is not the limiter at this size; it is for the syn-1M workload (default config)"}
+    out = {"metric": METRIC, "value": n_cells / (step_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "the reference's shipped input deck",
+           "config": {"workload": text, "cells": n_cells, "regular_elements": n_regular, "triangles": fp.n_tri, "dof": fp.n_dof,
+                      "coo_triplets": info["n_coo"], "nnz": info["nnz"], "rtol_true_residual": 1e-12,
+                      "l2": "problem smaller than L2 (the workload is what the reference ships); launch-latency bound", "parallelism": "1 GPU"},
+           "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+           "phases_ms_per_step": {k: v / steps for k, v in phases.items()},
+           "pcg": {"iterations": si["iterations"], "converged": si["converged"], "relres_true": si["relres_true"], "restarts": si["restarts"],
+                   "iterations_per_s": si["iterations"] / (phases["solve_ms"] / steps * 1e-3)},
+           "energy": last["energy"], "parity_check": parity}
+    emit(out)
+
+
+def rank_problem(n0, family, strong, rank, world, host_overlay=False):
+    """What rank ``rank`` of ``world`` holds of the N-GPU problem: its strip of the overlay (host build of the overlay core, before
+    CUDA / NCCL are up), partitioned by node owner.  Weak scaling: a stack of N blocks of n0 x n0 mesh-0 elements, one corner load
+    per block; strong: ONE n0 x n0 problem cut into N strips.  Returns (LocalPart, rhs, fixed, fixed_value in local numbering,
+    number of cells of the global problem this rank accounts for)."""
+    from mofem_b200.overlay_gen import patch_family
+    from mofem_b200.partition import partition_problem
+    px = n0 // 8                                  # patches per patch row
+    if strong:
+        if px % world:
+            raise SystemExit("--strong needs n0 / 8 to be a multiple of the number of GPUs")
+        ny, per = n0, px // world                 # one n0 x n0 problem, `per` patch rows (8 * per element rows) per rank
+    else:
+        ny, per = n0 * world, px                  # a stack of N blocks of n0 x n0
+    rows_per_rank = 8 * per
+    n_node0 = (n0 + 1) * (ny + 1)
+    if family == "quad":
+        strip, rhs_g, fixed_g, val_g = patch_family(n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per),
+                                                    engine="numpy" if host_overlay else "native")
+        owner = np.empty(strip.n_node, np.int32)
+        owner[:n_node0] = np.minimum((np.arange(n_node0) // (n0 + 1)) // rows_per_rank, world - 1)
+        owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // px) // per
+        # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
+        own_cells = strip.n_cell - (n0 if rank > 0 else 0)      # (one mesh-0 element row per strip boundary)
+    else:
+        # rank r owns the nodes whose nominal row lies in its element rows; it integrates every cell that touches one
+        # of them (the generator emits a margin of 3 element rows, the partitioner keeps what is needed)
+        from mofem_b200.overlay_gen import general_strip
+        strip, rhs_g, fixed_g, val_g, owner, own_cells = general_strip(n0, family, ny, rank, world)
+    # weak scaling keeps the physics per block fixed: every block carries the corner load of the 1-GPU problem on
+    # its own bottom-right node (a single load on a domain N times taller would need ~N times more CG iterations
+    # just to propagate across the height); strong scaling solves the one problem as it is
+    stack_loads(rhs_g, n0, 1 if strong else world)
+    part = partition_problem(strip, owner, rank, world)
+    return part, part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g), own_cells
+
+
+def stack_loads(rhs_g, n0, blocks):
+    for r in range(1, blocks):
+        nd = r * n0 * (n0 + 1) + n0
+        rhs_g[2 * nd] = 1.0; rhs_g[2 * nd + 1] = -0.5
+
+
+def global_problem(n0, family, strong, world):
+    """The same N-GPU problem as ONE flattened problem (for the single-GPU side of the parity check)."""
+    from mofem_b200.overlay_gen import general_family, patch_family
+    ny = n0 if strong else n0 * world
+    fp, rhs, fixed, val = patch_family(n0, ny=ny, engine="native") if family == "quad" else general_family(n0, family, ny=ny)
+    stack_loads(rhs, n0, 1 if strong else world)
+    return fp, rhs, fixed, val
+
+
+def multi_gpu_parity(args, rank, world, local, transport):
+    """Untimed, after the timed steps (N > 1): a reduced problem of the same family and layout (n0 = 64) solved on the N ranks with the
+    run's transport and on rank 0 alone; the gathered displacement and the energy must agree to 1e-9."""
+    import torch.distributed as dist
+    from mofem_b200.device import Context
+    from mofem_b200.distributed import assemble_solve_partitioned, gather_global, init_comm
+    from mofem_b200.partition import exchange_send_lists
+    n0 = 64
+    part, rhs, fixed, val, _ = rank_problem(n0, args.family, args.strong, rank, world)
+    exchange_send_lists(part)
+    with Context(local) as ctx:
+        init_comm(ctx)
+        u_loc, info, energy = assemble_solve_partitioned(ctx, part, rhs, fixed, val, rtol=1e-12, transport=transport)
+        if transport == "peer":
+            dist.barrier()
+            ctx.p2p_close()
+    n_node = int(part.local2global.max()) + 1
+    t = [None] * world
+    dist.all_gather_object(t, n_node)
+    n_node = max(t)
+    u = gather_global(part, u_loc, n_node)
+    if rank != 0:
+        return None
+    fp, rhs_g, fixed_g, val_g = global_problem(n0, args.family, args.strong, world)
+    assert fp.n_node == n_node
+    with Context(local) as ctx:
+        ctx.set_problem(fp).symbolic().assemble()
+        ctx.set_system(rhs_g, fixed_g, val_g)
+        u1, info1 = ctx.solve(rtol=1e-12)
+        e1 = ctx.energy()
+    du = float(np.abs(u - u1).max() / np.abs(u1).max())
+    de = float(abs(energy - e1) / abs(e1))
+    return {"problem": f"{args.family} family, n0 = {n0}, {'one block cut into' if args.strong else 'a stack of'} {world} {'strips' if args.strong else 'blocks'}: "
+                       f"{fp.n_cell} cells, {fp.n_dof} DOF; {world} ranks ({transport}) against rank 0 alone, rtol 1e-12",
+            "max_rel_du": du, "energy_rel": de, "n_ranks": world, "tolerance": 1e-9, "passed": bool(du <= 1e-9 and de <= 1e-9),
+            "iterations": {"ranks": info["iterations"], "single": info1["iterations"]},
+            "relres_true": {"ranks": info["relres_true"], "single": info1["relres_true"]}}
 
 
 def main():
@@ -230,7 +572,15 @@ def main():
     ap.add_argument("--n0", type=int, default=664, help="mesh-0 elements per side (664 -> ~1M overlay cells)")
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--ref-n0", type=int, default=256, help="size of the bounded CPU sample")
+    ap.add_argument("--ref-cells", type=int, default=20000, help="cells of the workload the unmodified reference integrates per sample (all cores)")
+    ap.add_argument("--ref-cells-1core", type=int, default=4000, help="cells of the single-process reference sample (cpu_baseline, cores = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-port-figure", action="store_true", help="skip the secondary CPU figure (oracle C port + scipy + spsolve at --ref-n0)")
+    ap.add_argument("--config", default="syn", choices=["syn", "bracket", "ofe3"],
+                    help="syn = the synthetic workload (default; BASELINE configs 3-5 by --n0 / --family / --gpus); bracket / ofe3 = the "
+                         "reference's shipped problems through its own parser and plane sweep, solver entry point swapped for the drop-in "
+                         "(BASELINE configs 2 / 1), timed against the unmodified reference in full")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the untimed N-ranks-against-one parity solve after the timed steps")
     ap.add_argument("--no-profile", action="store_true", help="do not record per-kernel events inside the PCG loop")
     ap.add_argument("--profile-every", type=int, default=16,
                     help="record CUDA events around the PCG kernels of every N-th iteration of the timed steps (1 = all; the "
@@ -257,6 +607,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "syn":
+        return run_shipped(args)
 
     import torch
     import torch.distributed as dist
@@ -294,39 +646,9 @@ def main():
         fp, rhs, fixed, val = patch_family(args.n0)
     else:
         from mofem_b200.distributed import init_comm
-        from mofem_b200.partition import exchange_send_lists, partition_problem
-        px = args.n0 // 8                                  # patches per patch row
-        if args.strong:
-            if px % world:
-                raise SystemExit("--strong needs n0 / 8 to be a multiple of the number of GPUs")
-            ny, per = args.n0, px // world                 # one n0 x n0 problem, `per` patch rows (8 * per element rows) per rank
-        else:
-            ny, per = args.n0 * world, px                  # a stack of N blocks of n0 x n0
-        rows_per_rank = 8 * per
-        n_node0 = (args.n0 + 1) * (ny + 1)
-        if args.family == "quad":
-            strip, rhs_g, fixed_g, val_g = patch_family(args.n0, ny=ny, patch_rows=(rank * per, (rank + 1) * per),
-                                                        engine="numpy" if args.host_overlay else "native")
-            owner = np.empty(strip.n_node, np.int32)
-            owner[:n_node0] = np.minimum((np.arange(n_node0) // (args.n0 + 1)) // rows_per_rank, world - 1)
-            owner[n_node0:] = ((np.arange(strip.n_node - n_node0) // 36) // px) // per
-            # cells of the global problem = owned-strip cells, not counting the redundantly integrated boundary row
-            own_cells = strip.n_cell - (args.n0 if rank > 0 else 0)      # (one mesh-0 element row per strip boundary)
-        else:
-            # rank r owns the nodes whose nominal row lies in its element rows; it integrates every cell that touches one
-            # of them (the generator emits a margin of 3 element rows, the partitioner keeps what is needed)
-            from mofem_b200.overlay_gen import general_strip
-            strip, rhs_g, fixed_g, val_g, owner, own_cells = general_strip(args.n0, args.family, ny, rank, world)
-        # weak scaling keeps the physics per block fixed: every block carries the corner load of the 1-GPU problem on
-        # its own bottom-right node (a single load on a domain N times taller would need ~N times more CG iterations
-        # just to propagate across the height); strong scaling solves the one problem as it is
-        for r in range(1, world if not args.strong else 1):
-            nd = r * args.n0 * (args.n0 + 1) + args.n0
-            rhs_g[2 * nd] = 1.0; rhs_g[2 * nd + 1] = -0.5
-        part = partition_problem(strip, owner, rank, world)
+        from mofem_b200.partition import exchange_send_lists
+        part, rhs, fixed, val, own_cells = rank_problem(args.n0, args.family, args.strong, rank, world, args.host_overlay)
         fp = part.fp
-        rhs, fixed, val = part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g)
-        del strip, rhs_g, fixed_g, val_g, owner
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -421,7 +743,6 @@ def main():
         t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms = float(t.item())
-    info = ctx.info()
     si = last["solve"]
 
     # ---- end to end through the public API with pinned host buffers -----------------------------------------------
@@ -444,6 +765,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     assert np.array_equal(u_h, u_d.cpu().numpy()), "host-buffer path and resident path must give identical bits"
+
+    info = ctx.info()
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        if transport == "peer":
+            barrier()
+            ctx.p2p_close()
+        ctx.clear_halo()
+        parity = multi_gpu_parity(args, rank, world, local, transport)
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -468,6 +799,8 @@ def main():
                     "bound": "hbm", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                     "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                    "traffic_source": (f"committed ncu --set full capture of this kernel on this workload ({os.path.relpath(tpath, REPO)}: dram__bytes_read.sum + "
+                                       "dram__bytes_write.sum of one launch), not measured in this run") if traffic is not None else None,
                     "algorithmic_bytes_per_launch": ab["spmv"], "avg_launch_ms": spmv_ms,
                     "scalar_csr_equivalent_gbs": ab["spmv_scalar_csr"] / (spmv_ms * 1e-3) / 1e9,
                     "share_of_step": spmv_ms * si["iterations"] / step_ms,
@@ -487,8 +820,8 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        log("timing the CPU baseline (oracle port + scipy) ...")
-        cpu = cpu_baseline(args.ref_n0)
+        log("timing the CPU baseline (unmodified reference on a subsample of the workload; oracle port + scipy) ...")
+        cpu = cpu_baseline(fp, args)
 
     cells_total = fp.n_cell if world == 1 else n_cells_global
     out = {
@@ -496,8 +829,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"syn-{max(1, round(cells_total / (1 if args.strong else world) / 1e6))}M patch-family overlay ({FAMILY_TEXT[args.family]}, jitter 0.12h): assembly + Jacobi-PCG",
-                   "n0": args.n0, "cells": fp.n_cell, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"],
-                   "nnz": info["nnz"], "rtol_true_residual": args.rtol,
+                   "n0": args.n0, "cells": cells_total, "triangles": fp.n_tri, "dof": fp.n_dof, "coo_triplets": info["n_coo"], "nnz": info["nnz"],
+                   "per_rank_fields": None if world == 1 else "triangles, dof, coo_triplets, nnz are rank 0's share (cells is the global count)",
+                   "rtol_true_residual": args.rtol,
                    "l2": f"inputs larger than L2 (per GPU: CSR {9 * info['nnz'] / 1e9:.2f} GB, block values {32 * info['n_pair'] / 1e9:.2f} GB vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else
                    f"{world} GPUs: cells sharded by strip (no assembly exchange), row-partitioned PCG, halo "
@@ -517,6 +851,7 @@ def main():
                 "restarts": si["restarts"], "iterations_per_s": si["iterations"] / (phases["solve_ms"] / args.steps * 1e-3)},
         "kernels": kernels,
         "energy": last["energy"],
+        "parity_check": parity,
         "prep_s": prep_s,
         "overlay": ({"where": "gpu (csrc/overlay.cu, pairwise convex clipping)", "kernels_ms": overlay_ms} if overlay_ms is not None
                     else {"where": "host, NumPy generator (mofem_b200/overlay_gen.py)" if args.host_overlay or world == 1

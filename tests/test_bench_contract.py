@@ -10,7 +10,7 @@ from conftest import REPO
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-n0", "16"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "0", "--n0", "16", "--ref-cells", "60"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -18,7 +18,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("overlay-cell stiffness assembly cells/s")
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.isdir(os.path.join(REPO, "baseline", "_ref", "MOFEM"))      # the unmodified reference when staged, else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 
@@ -26,7 +27,7 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_exit_silently():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                          "--warmup", "0", "--ref-n0", "16"], capture_output=True, text=True, timeout=300, env=env)
+                          "--warmup", "0", "--n0", "16", "--ref-cells", "60"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 

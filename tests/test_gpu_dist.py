@@ -100,6 +100,31 @@ def test_four_gpu_solve_matches_single_gpu(gpu_ctx, transport):
         assert np.array_equal(res[0][0], res[r][0])
 
 
+@pytest.mark.parametrize("transport", ["peer"])
+def test_eight_gpu_solve_matches_single_gpu(gpu_ctx, transport):
+    import torch
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    import torch.multiprocessing as mp
+    from mofem_b200 import overlay_gen
+    ny = 128
+    fp, rhs, fixed, val = overlay_gen.patch_family(NX, ny=ny)
+    gpu_ctx.clear_halo()
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    gpu_ctx.set_system(rhs, fixed, val)
+    u1, info1 = gpu_ctx.solve(rtol=1e-12)
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(8, port, out, transport, ny), nprocs=8, join=True)
+        res = [out[r] for r in range(8)]
+    for u, info, energy in res:
+        assert info["converged"] == 1
+        assert np.abs(u - u1).max() <= 1e-9 * np.abs(u1).max()
+    for r in range(1, 8):
+        assert np.array_equal(res[0][0], res[r][0])
+
+
 def test_halo_plan_with_no_neighbours_is_the_single_gpu_path(gpu_ctx):
     """world = 1: the partitioned entry points reduce to the plain solve."""
     from mofem_b200 import overlay_gen

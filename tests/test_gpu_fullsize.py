@@ -33,7 +33,7 @@ def test_sizes_match_the_survey(big, gpu_ctx):
         return
     if fp.family == "m3s":      # cells with 1, 2 and 3 incident elements
         m = (fp.cell_elem >= 0).sum(1)[fp.cell_kind == 1]
-        assert fp.n_mesh == 3 and np.bincount(m)[1:].min() > 2e5 and 1.6e6 < fp.n_cell < 1.8e6
+        assert fp.n_mesh == 3 and np.bincount(m)[1:].min() > 5e4 and 1.6e6 < fp.n_cell < 1.8e6
         return
     assert fp.n_dof == 2 * (665 ** 2 + 6889 * 36) == info["n_dof"]
     # per patch period 28672 COO triplets, of which 28 untouched quadFE cells * 64
