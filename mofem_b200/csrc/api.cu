@@ -41,7 +41,7 @@ struct mofem_ctx {
     int spmv_ring = 1;    // PCG SpMV streams the matrix through shared memory with the TMA (spmv_ring.cuh); 0: row kernel
     double floor_rtol = 1e-8;   // largest true relative residual mofem_solve accepts as "fp64 floor reached" (converged = 2)
     int pdl = 1;          // programmatic dependent launch between the two kernels of a PCG iteration (single GPU, peer transport)
-    int cell_kernel = 0;  // 1: quad4 overlay cells on the warp-cooperative cell kernel (bit-identical, measured slower: 3.1 vs 2.55 ms at syn-1M)
+    int cell_kernel = 1;  // 1: all-quad4 overlay cells on the cell kernel (one evaluation per (point, element); bit-identical to the thread-per-block kernels, 0)
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms[6]{};
@@ -330,8 +330,18 @@ int mofem_assemble(mofem_ctx *ctx)
     CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * 4, s));
     tic(ctx);
     for (int k = 0; k < N_CLASS; k++) {
+        if (k == FAST_CLASS) {      // one launch per (incident elements, triangles) sub-bucket; the last sub-bucket holds no first tasks
+            for (int b = 0; b < N_SUB - 1; b++) {
+                const int64_t n = ctx->cls_count[k * N_SUB + b];
+                if (!n) continue;
+                CK(launch_cell_quads(b / 5 + 1, b % 5 + 1, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB + b], n, ctx->blk_val,
+                                     ctx->stats, s));
+                ctx->launches[1]++;
+            }
+            continue;
+        }
         int64_t n_cls = 0;
-        for (int b = 0; b < (k == FAST_CLASS ? 1 : N_SUB); b++) n_cls += ctx->cls_count[k * N_SUB + b];   // FAST: first tasks only
+        for (int b = 0; b < N_SUB; b++) n_cls += ctx->cls_count[k * N_SUB + b];
         if (!n_cls) continue;
         CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB], n_cls, ctx->blk_val,
                                   ctx->stats, s));

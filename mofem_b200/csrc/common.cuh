@@ -21,7 +21,7 @@ constexpr int N_CLASS = 8 + 32;
 // tasks of one class are further grouped by (diagonal / off-diagonal, triangle count) so that the threads of a warp
 // run the same trip counts; a bucket id is class * N_SUB + sub
 constexpr int N_SUB = 16;
-constexpr int FAST_CLASS = 5;   // quad4 overlay cells on the warp-cooperative cell kernel (sub-bucket 0 = first task of a cell)
+constexpr int FAST_CLASS = 5;   // all-quad4 overlay cells on the cell kernel: sub-bucket (ne-1)*5 + T-1 = first tasks of the cells with ne elements / T triangles
 constexpr int N_BUCKET = N_CLASS * N_SUB;
 __host__ __device__ inline int type_index(int nn) { return nn == 3 ? 0 : nn == 4 ? 1 : nn == 6 ? 2 : 3; }
 
@@ -73,6 +73,11 @@ cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS
 // integrates all tasks of one class; stats[0] += newton updates, stats[1] += evaluations, stats[2] = error flag
 cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *task_list,
                                    int64_t n_list, double *blk_val, unsigned long long *stats, cudaStream_t s);
+
+// all-quad4 overlay cells with ne incident elements and T straight triangles (first tasks in `first_task`): one evaluation per
+// (point, element), blocks contracted out of shared memory
+cudaError_t launch_cell_quads(int ne, int T, const DevProblem &p, const DevTasks &t, const int32_t *first_task, int64_t n_cells,
+                              double *blk_val, unsigned long long *stats, cudaStream_t s);
 
 // csr.cu
 struct DevCsr {

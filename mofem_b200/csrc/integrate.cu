@@ -164,24 +164,27 @@ __device__ __forceinline__ int task_class(const DevProblem &p, int64_t c, int n1
     return 8 + 2 * (4 * type_index(n1) + type_index(n2)) + curved;
 }
 
-// Cells whose incident elements are one or two 4-node quads, integrated over straight triangles, take the warp-cooperative
-// cell kernel (k_cell_q4): all their tasks go to class FAST_CLASS, sub-bucket 0 = the first task of the cell.
-__device__ __forceinline__ bool cell_is_fast(const DevProblem &p, int64_t c)
+// Overlay cells whose incident elements (1..3) are all 4-node quads, integrated over 1..5 straight triangles, take the cell
+// kernel (k_cell_quads): all their tasks go to class FAST_CLASS; sub-bucket (ne - 1) * 5 + (T - 1) holds the FIRST task of each
+// such cell (one launch per (ne, T)), sub-bucket 15 the remaining tasks (never iterated).  Returns the sub-bucket or -1.
+__device__ __forceinline__ int cell_fast_sub(const DevProblem &p, int64_t c)
 {
-    if (p.cell_kind[c] != CELL_OVERLAY) return false;
+    if (p.cell_kind[c] != CELL_OVERLAY) return -1;
     const int32_t *ce = p.cell_elem + c * p.n_mesh;
     int ne = 0;
     for (int j = 0; j < p.n_mesh; j++)
-        if (ce[j] >= 0) { if (p.elem_nn[ce[j]] != 4) return false; ne++; }
-    if (ne < 1 || ne > 2) return false;
+        if (ce[j] >= 0) { if (p.elem_nn[ce[j]] != 4) return -1; ne++; }
+    if (ne < 1 || ne > 3) return -1;
+    const int64_t nt = p.cell_tri_ptr[c + 1] - p.cell_tri_ptr[c];
+    if (nt < 1 || nt > 5) return -1;
     if (p.tri_curved)
-        for (int64_t t = p.cell_tri_ptr[c]; t < p.cell_tri_ptr[c + 1]; t++) if (p.tri_curved[t]) return false;
-    return p.cell_tri_ptr[c + 1] > p.cell_tri_ptr[c];
+        for (int64_t t = p.cell_tri_ptr[c]; t < p.cell_tri_ptr[c + 1]; t++) if (p.tri_curved[t]) return -1;
+    return (ne - 1) * 5 + (int)nt - 1;
 }
 
-__device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n1, int n2, bool regular, bool diag, int fast = 0)
+__device__ __forceinline__ int task_bucket(const DevProblem &p, int64_t c, int n1, int n2, bool regular, bool diag, int fast = -1)
 {
-    if (fast) return FAST_CLASS * N_SUB + (fast == 1 ? 0 : 1);
+    if (fast >= 0) return FAST_CLASS * N_SUB + fast;
     const int cls = task_class(p, c, n1, n2, regular);
     int sub = 0;
     if (!regular) {
@@ -209,19 +212,19 @@ __global__ void k_fill_tasks(DevProblem p, const int64_t *__restrict__ task_off,
             }
         return;
     }
-    const bool fast = use_fast && cell_is_fast(p, c);
+    const int fsub = use_fast ? cell_fast_sub(p, c) : -1;
     const int64_t k0 = k;
     for (int j = 0; j < M; j++) {
         if (ce[j] < 0) continue;
         int n1 = p.elem_nn[ce[j]];
         t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[j]; t.slots[k] = j | (j << 8);
-        t.cls[k] = task_bucket(p, c, n1, n1, false, true, fast ? (k == k0 ? 1 : 2) : 0); t.pair_off[k] = po;
+        t.cls[k] = task_bucket(p, c, n1, n1, false, true, fsub < 0 ? -1 : (k == k0 ? fsub : N_SUB - 1)); t.pair_off[k] = po;
         k++; po += n1 * n1;
         for (int l = j + 1; l < M; l++) {
             if (ce[l] < 0) continue;
             int n2 = p.elem_nn[ce[l]];
             t.cell[k] = (int32_t)c; t.e1[k] = ce[j]; t.e2[k] = ce[l]; t.slots[k] = j | (l << 8);
-            t.cls[k] = task_bucket(p, c, n1, n2, false, false, fast ? 2 : 0); t.pair_off[k] = po;
+            t.cls[k] = task_bucket(p, c, n1, n2, false, false, fsub < 0 ? -1 : N_SUB - 1); t.pair_off[k] = po;
             k++; po += n1 * n2;
         }
     }
@@ -417,126 +420,170 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Warp-cooperative cell kernel for the dominant case: overlay cells whose incident elements are one or two 4-node quads,
-// straight integration triangles (stiffnessMatrix.lowerOrderAMORE:99 / quadraticAMORE:131 with n1 + n2 = 8 -> 6 points).
+// Cell kernel for the dominant case: overlay cells whose NE <= 3 incident elements are all 4-node quads, integrated over
+// T <= 5 straight triangles (stiffnessMatrix.lowerOrderAMORE:99 / quadraticAMORE:131 with n1 + n2 = 8 -> the 6-point rule for
+// EVERY block of the cell, so all blocks share their integration points).
 //
-// Half a warp (16 lanes) owns one cell.
-//   phase 1  lane q < 16 takes integration point q of the round (points are numbered triangle-major, 6 per triangle):
-//            position, weights rho, ONE evaluation per incident element (Newton inverse map + shape gradients) -- the
-//            reference evaluates element j for its diagonal block and again for the off-diagonal block; the values are
-//            identical, so each (point, element) pair is evaluated once here -- and writes w*g and g of both elements
-//            to shared memory (32 doubles per point).
-//   phase 2  lane t < 4 * (blocks of the cell) owns row-node a of one block (diag j | off (j,l) | diag l) and accumulates
-//            its 4 x 4 sums over the points of the round IN POINT ORDER with the same fma sequence as k_amore, so the
-//            results are bit-identical to the thread-per-block kernel.
-// Geometry is staged through shared memory, the per-cell reduction is a shared-memory transpose (no atomics).
+// The reference evaluates the strain matrix of element j at every point once for the diagonal block (j,j) and again for every
+// off-diagonal block it takes part in (AMORE.py:59-123): NE evaluations per (point, element).  The values are identical, so here
+// each (point, element) pair is evaluated ONCE.  A CTA takes a batch of CB cells and runs three phases over shared memory:
+//   phase 0  thread per (cell, element): node coordinates -> smem; thread per (cell, triangle, element): det J of the triangle
+//            and grad(rho_e) (constant on a straight triangle) -> smem.
+//   phase 1  thread per EVALUATION (cell, point, element): position, rho, Newton inverse map, shape gradients, the compressed
+//            strain pair (gx[4], gy[4]) -> one 64-byte row in smem.  Short dependent chains at a register count that allows
+//            24 warps per SM: this is where the fp64 pipe is kept busy.
+//   phase 2  two threads per BLOCK (diag j | off (j,l)), each owning two row nodes = 32 of the block's 64 sums: they walk the
+//            points IN ORDER and accumulate with the same fma sequence as k_amore, reading the rows of elements j and l from
+//            smem, then apply D and store the 2x2 sub-blocks.  Results are bit-identical to the thread-per-block kernel.
+// Cell rows are padded by 16 bytes so that the lanes of different cells hit different banks.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int CELLQ_THREADS = 128;            // 8 cells per block
-constexpr int CELLQ_PT_DOUBLES = 32;          // per point: wg1x[4] wg1y[4] g1x[4] g1y[4] wg2x[4] wg2y[4] g2x[4] g2y[4]
+constexpr int CQ_THREADS = 256;
+constexpr int CQ_MAX_T = 5;                   // triangles per cell handled here (sub-bucket = (NE - 1) * 5 + T - 1)
+constexpr int CQ_SMEM_BUDGET = 72 * 1024;     // per CTA: 3 CTAs per SM
 
-__global__ void __launch_bounds__(CELLQ_THREADS, 4)
-k_cell_q4(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n_cells, double *__restrict__ blk_val,
-          unsigned long long *__restrict__ stats)
+__host__ __device__ inline int cq_row_stride(int ne, int T) { return ne * T * 6 * 8 + 2; }   // doubles per cell in `rows`
+__host__ __device__ inline int cq_cell_doubles(int ne, int T)
+{   // rows + detJ[T] + drho[T][ne][2] + exy[ne][8] + meta (ne + 3 ints, rounded up to doubles)
+    return cq_row_stride(ne, T) + T + T * ne * 2 + ne * 8 + (2 * ne + 3 + 1) / 2;
+}
+
+template <int NE>
+__global__ void __launch_bounds__(CQ_THREADS, 3)
+k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n_cells, int T, int CB,
+             double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
 {
-    __shared__ double pts[CELLQ_THREADS / 16][16][CELLQ_PT_DOUBLES];
-    const int lane = threadIdx.x & 15, slot = threadIdx.x >> 4;
-    const int64_t ci = (int64_t)blockIdx.x * (CELLQ_THREADS / 16) + slot;
-    const bool live = ci < n_cells;
+    extern __shared__ double sm[];
+    constexpr int TPC = NE * (NE + 1) / 2;                 // blocks (tasks) per cell
+    const int EPC = NE * T * 6;                            // evaluations per cell
+    const int RS = cq_row_stride(NE, T);
+    double *rows = sm;                                     // [CB][RS]
+    double *detj = rows + (size_t)CB * RS;                 // [CB][T]
+    double *drho = detj + CB * T;                          // [CB][T][NE][2]
+    double *exy = drho + CB * T * NE * 2;                  // [CB][NE][8]   X[4] Y[4]
+    int32_t *meta = reinterpret_cast<int32_t *>(exy + CB * NE * 8);   // [CB][2 NE + 3]: k0, tri0 (lo, hi), elem[NE], slot[NE]
+    constexpr int MS = 2 * NE + 3;
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * CB;
+    const int nb = (int)(n_cells - c0 < CB ? n_cells - c0 : CB);
+    const int M = p.n_mesh;
     unsigned long long newton = 0, evals = 0;
     bool fail = false;
-    int64_t k0 = 0, c = 0;
-    int e1 = 0, e2 = 0, sj = 0, sl = 0, ne = 1;
-    if (live) {
-        k0 = first_task[ci];
-        c = t.cell[k0];
-        e1 = t.e1[k0]; sj = t.slots[k0] & 0xff;
-        // a second incident element shows up as the off-diagonal task right after the diagonal one
-        if (k0 + 1 < t.n_task && t.cell[k0 + 1] == c) { ne = 2; e2 = t.e2[k0 + 1]; sl = t.slots[k0 + 1] >> 8; }
-        else { e2 = e1; sl = sj; }
-    }
-    double X1[4], Y1[4], X2[4], Y2[4];
-    if (live) { load_elem<4>(p, e1, X1, Y1); load_elem<4>(p, e2, X2, Y2); }
-    const int64_t tr0 = live ? p.cell_tri_ptr[c] : 0;
-    const int npts = live ? (int)(p.cell_tri_ptr[c + 1] - tr0) * 6 : 0;
-    const int M = p.n_mesh;
-    const int qoff = tri_rule_offset(6);
-    // phase-2 role of this lane
-    const int n_out = ne == 2 ? 12 : 4;
-    const int blk = lane >> 2, a = lane & 3;          // blk 0: diag j, 1: off (j,l), 2: diag l
-    const int wsrc = (blk == 2) ? 16 : 0;             // w*g of element l for the last block, of element j otherwise
-    const int gsrc = (blk == 0) ? 8 : 24;             // g of element j for the first block, of element l otherwise
-    double S[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) S[i] = 0.0;
-    // all 32 lanes of the warp run the same number of rounds (the two cells of a warp may differ)
-    const int npts_other = __shfl_xor_sync(0xffffffffu, npts, 16);
-    const int rounds = ((npts > npts_other ? npts : npts_other) + 15) >> 4;
-    for (int r = 0; r < rounds; r++) {
-        const int q = r * 16 + lane;
-        if (q < npts) {
-            const int64_t tr = tr0 + q / 6;
-            const int kq = q % 6;
-            double tx[3], ty[3], rho1[3], rho2[3];
-#pragma unroll
-            for (int v = 0; v < 3; v++) {
-                tx[v] = p.tri_xy[6 * tr + 2 * v]; ty[v] = p.tri_xy[6 * tr + 2 * v + 1];
-                rho1[v] = p.tri_rho[(3 * tr + v) * M + sj];
-                rho2[v] = p.tri_rho[(3 * tr + v) * M + sl];
-            }
-            TriPoint tp;
-            tri_straight(tx, ty, tp);
-            double dr1x, dr1y, dr2x = 0.0, dr2y = 0.0;
-            tri_grad_rho(tp, rho1, dr1x, dr1y);
-            if (ne == 2) tri_grad_rho(tp, rho2, dr2x, dr2y);
-            const double L1 = c_tp[3 * (qoff + kq)], L2 = c_tp[3 * (qoff + kq) + 1];
-            const double wq = c_tw[qoff + kq];
-            double Nt[3] = {L1, L2, 1.0 - L1 - L2};
-            const double x = dot_vecmat<3>(Nt, tx), y = dot_vecmat<3>(Nt, ty);
-            const double r1v = dot_gemm<3>(Nt, rho1);
-            const double w = 0.5 * tp.detJ * wq;
-            double gx[4], gy[4];
-            int it = strain_pair<4>(X1, Y1, x, y, r1v, dr1x, dr1y, gx, gy);
-            if (it < 0) fail = true; else newton += (unsigned long long)it * (ne == 2 ? 2 : 1);   // the reference evaluates twice
-            evals += (ne == 2 ? 2 : 1);
-            double *row = pts[slot][lane];
-#pragma unroll
-            for (int b = 0; b < 4; b++) { row[b] = w * gx[b]; row[4 + b] = w * gy[b]; row[8 + b] = gx[b]; row[12 + b] = gy[b]; }
-            if (ne == 2) {
-                const double r2v = dot_gemm<3>(Nt, rho2);
-                it = strain_pair<4>(X2, Y2, x, y, r2v, dr2x, dr2y, gx, gy);
-                if (it < 0) fail = true; else newton += 2ull * it;
-                evals += 2;
-#pragma unroll
-                for (int b = 0; b < 4; b++) { row[16 + b] = w * gx[b]; row[20 + b] = w * gy[b]; row[24 + b] = gx[b]; row[28 + b] = gy[b]; }
-            }
+
+    // ---- phase 0a: per cell -> first task, first triangle, element ids, mesh slots; per (cell, element) -> node coordinates
+    for (int i = tid; i < nb * NE; i += CQ_THREADS) {
+        const int ci = i / NE, e = i - ci * NE;
+        const int64_t k0 = first_task[c0 + ci];
+        // the diagonal task of element e inside the cell's task run: (0) | (0, 2) | (0, 3, 5)
+        const int dt = (NE == 1) ? 0 : (NE == 2) ? 2 * e : (e == 0 ? 0 : e == 1 ? 3 : 5);
+        const int el = t.e1[k0 + dt];
+        int32_t *m = meta + ci * MS;
+        if (e == 0) {
+            const int64_t tr0 = p.cell_tri_ptr[t.cell[k0]];
+            m[0] = (int32_t)k0; m[1] = (int32_t)(tr0 & 0xffffffffll); m[2] = (int32_t)(tr0 >> 32);
         }
-        __syncwarp();
-        if (live && lane < n_out) {
-            const int nq = npts - r * 16 < 16 ? npts - r * 16 : 16;
-            for (int qq = 0; qq < nq; qq++) {
-                const double *row = pts[slot][qq];
-                const double wx = row[wsrc + a], wy = row[wsrc + 4 + a];
+        m[3 + e] = el;
+        m[3 + NE + e] = t.slots[k0 + dt] & 0xff;
+        double *xy = exy + (ci * NE + e) * 8;
+        const int32_t *en = p.elem_nodes + (int64_t)el * 9;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const double2 v = *reinterpret_cast<const double2 *>(p.node_xy + 2 * (int64_t)en[a]);
+            xy[a] = v.x; xy[4 + a] = v.y;
+        }
+    }
+    __syncthreads();
+    // ---- phase 0b: per (cell, triangle, element) -> det J, grad(rho_e)
+    for (int i = tid; i < nb * T * NE; i += CQ_THREADS) {
+        const int ci = i / (T * NE), r = i - ci * (T * NE), tr = r / NE, e = r - tr * NE;
+        const int32_t *m = meta + ci * MS;
+        const int64_t trg = (((int64_t)m[2] << 32) | (uint32_t)m[1]) + tr;
+        const int slot = m[3 + NE + e];
+        double tx[3], ty[3], rho[3];
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            tx[v] = p.tri_xy[6 * trg + 2 * v]; ty[v] = p.tri_xy[6 * trg + 2 * v + 1];
+            rho[v] = p.tri_rho[(3 * trg + v) * M + slot];
+        }
+        TriPoint tp;
+        tri_straight(tx, ty, tp);
+        double gx, gy;
+        tri_grad_rho(tp, rho, gx, gy);
+        if (e == 0) detj[ci * T + tr] = tp.detJ;
+        drho[((ci * T + tr) * NE + e) * 2] = gx;
+        drho[((ci * T + tr) * NE + e) * 2 + 1] = gy;
+    }
+    __syncthreads();
+    // ---- phase 1: one evaluation per (cell, point, element)
+    const int qoff = tri_rule_offset(6);
+    for (int ev = tid; ev < nb * EPC; ev += CQ_THREADS) {
+        const int ci = ev / EPC, rem = ev - ci * EPC, q = rem / NE, e = rem - q * NE, tr = q / 6, kq = q - tr * 6;
+        const int32_t *m = meta + ci * MS;
+        const int64_t trg = (((int64_t)m[2] << 32) | (uint32_t)m[1]) + tr;
+        const int slot = m[3 + NE + e];
+        double tx[3], ty[3], rho[3];
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            tx[v] = p.tri_xy[6 * trg + 2 * v]; ty[v] = p.tri_xy[6 * trg + 2 * v + 1];
+            rho[v] = p.tri_rho[(3 * trg + v) * M + slot];
+        }
+        const double L1 = c_tp[3 * (qoff + kq)], L2 = c_tp[3 * (qoff + kq) + 1];
+        double Nt[3] = {L1, L2, 1.0 - L1 - L2};
+        const double x = dot_vecmat<3>(Nt, tx), y = dot_vecmat<3>(Nt, ty);
+        const double rv = dot_gemm<3>(Nt, rho);
+        const double *dr = drho + ((ci * T + tr) * NE + e) * 2;
+        const double *xy = exy + (ci * NE + e) * 8;
+        double X[4], Y[4], gx[4], gy[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) { X[a] = xy[a]; Y[a] = xy[4 + a]; }
+        const int it = strain_pair<4>(X, Y, x, y, rv, dr[0], dr[1], gx, gy);
+        if (it < 0) fail = true; else newton += (unsigned long long)it * NE;     // the reference evaluates NE times (1 diag + NE-1 off)
+        evals += NE;
+        double2 *row = reinterpret_cast<double2 *>(rows + (size_t)ci * RS + (q * NE + e) * 8);
+        row[0] = make_double2(gx[0], gx[1]); row[1] = make_double2(gx[2], gx[3]);
+        row[2] = make_double2(gy[0], gy[1]); row[3] = make_double2(gy[2], gy[3]);
+    }
+    __syncthreads();
+    // ---- phase 2: two threads per block, 2 row nodes x 4 column nodes x 4 sums each
+    if (tid < nb * TPC * 2) {
+        const int ci = tid / (TPC * 2), r = tid - ci * (TPC * 2), tk = r >> 1, h = r & 1;
+        int ej, el;
+        if (NE == 1) { ej = 0; el = 0; }
+        else if (NE == 2) { ej = tk == 2 ? 1 : 0; el = tk == 0 ? 0 : 1; }
+        else { ej = tk < 3 ? 0 : (tk < 5 ? 1 : 2); el = tk < 3 ? tk : (tk < 5 ? tk - 2 : 2); }
+        const double *base = rows + (size_t)ci * RS;
+        double S[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) S[i] = 0.0;
+        const int npt = T * 6;
+        for (int q = 0; q < npt; q++) {
+            const int tr = q / 6, kq = q - tr * 6;
+            const double w = 0.5 * detj[ci * T + tr] * c_tw[qoff + kq];
+            const double2 *r1 = reinterpret_cast<const double2 *>(base + (q * NE + ej) * 8);
+            const double2 *r2 = reinterpret_cast<const double2 *>(base + (q * NE + el) * 8);
+            const double2 a_x = r1[h], a_y = r1[2 + h];                  // g1x, g1y of row nodes 2h, 2h+1
+            const double2 b0 = r2[0], b1 = r2[1], b2 = r2[2], b3 = r2[3];
+            const double g2x[4] = {b0.x, b0.y, b1.x, b1.y}, g2y[4] = {b2.x, b2.y, b3.x, b3.y};
+            const double wx[2] = {w * a_x.x, w * a_x.y}, wy[2] = {w * a_y.x, w * a_y.y};
+#pragma unroll
+            for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const double g2x = row[gsrc + b], g2y = row[gsrc + 4 + b];
-                    S[4 * b + 0] = fma(wx, g2x, S[4 * b + 0]);
-                    S[4 * b + 1] = fma(wx, g2y, S[4 * b + 1]);
-                    S[4 * b + 2] = fma(wy, g2x, S[4 * b + 2]);
-                    S[4 * b + 3] = fma(wy, g2y, S[4 * b + 3]);
+                    double *s4 = S + 4 * (a * 4 + b);
+                    s4[0] = fma(wx[a], g2x[b], s4[0]);
+                    s4[1] = fma(wx[a], g2y[b], s4[1]);
+                    s4[2] = fma(wy[a], g2x[b], s4[2]);
+                    s4[3] = fma(wy[a], g2y[b], s4[3]);
                 }
-            }
         }
-        __syncwarp();
-    }
-    if (live && lane < n_out) {
-        // diag j and off (j,l) use element j's material (AMORE.py:113), diag l its own
-        const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[blk == 2 ? e2 : e1];
+        const int32_t *m = meta + ci * MS;
+        // diag j and off (j,l) use element j's material (AMORE.py:113)
+        const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[m[3 + ej]];
         double D[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
-        double *out = blk_val + 4 * (t.pair_off[k0 + blk] + 4 * a);
+        double *out = blk_val + 4 * (t.pair_off[(int64_t)m[0] + tk] + 8 * h);
 #pragma unroll
-        for (int b = 0; b < 4; b++) store_pair(out + 4 * b, D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3]);
+        for (int ab = 0; ab < 8; ab++) store_pair(out + 4 * ab, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -548,6 +595,34 @@ k_cell_q4(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int6
         if (evals) atomicAdd(&stats[1], evals);
     }
     if (fail) stats[2] = 1;
+}
+
+template <int NE>
+static cudaError_t launch_cell_quads_ne(int T, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
+                                        double *blk_val, unsigned long long *stats, cudaStream_t s)
+{
+    constexpr int TPC = NE * (NE + 1) / 2;
+    const int per_cell = cq_cell_doubles(NE, T) * 8;
+    int CB = CQ_THREADS / 2 / TPC;
+    if (CB > CQ_SMEM_BUDGET / per_cell) CB = CQ_SMEM_BUDGET / per_cell;
+    if (CB < 1) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)CB * per_cell + 64;
+    cudaError_t e = cudaFuncSetAttribute(k_cell_quads<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_SMEM_BUDGET + 64);
+    if (e != cudaSuccess) return e;
+    k_cell_quads<NE><<<(unsigned)((n + CB - 1) / CB), CQ_THREADS, smem, s>>>(p, t, list, n, T, CB, blk_val, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cell_quads(int ne, int T, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
+                              double *blk_val, unsigned long long *stats, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    switch (ne) {
+    case 1: return launch_cell_quads_ne<1>(T, p, t, list, n, blk_val, stats, s);
+    case 2: return launch_cell_quads_ne<2>(T, p, t, list, n, blk_val, stats, s);
+    case 3: return launch_cell_quads_ne<3>(T, p, t, list, n, blk_val, stats, s);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 // Regular elements: triFE (1 pt) / triQuadFE (3 pts) / quadFE (2x2) / quadQuadFE (3x3), stiffnessMatrix.py:9-81.
@@ -714,10 +789,7 @@ cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks 
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (cls == FAST_CLASS) {
-        k_cell_q4<<<(unsigned)((n + CELLQ_THREADS / 16 - 1) / (CELLQ_THREADS / 16)), CELLQ_THREADS, 0, s>>>(p, t, list, n, blk_val, stats);
-        return cudaGetLastError();
-    }
+    if (cls == FAST_CLASS) return cudaErrorInvalidValue;      // launch_cell_quads, one launch per (ne, T) sub-bucket
     if (cls < 8) {
         switch (cls) {
         case 0: k_regular<3><<<grid, 128, 0, s>>>(p, t, list, n, blk_val); break;

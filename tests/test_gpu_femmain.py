@@ -30,11 +30,11 @@ def test_femmain_bracket_with_the_drop_in(tmp_path):
     assert {"solution.txt", "SampleData.txt", "nSampling.txt", "boundaryCoord.txt", "boundaryNumber.txt"} <= set(out["files"])
     assert set(out["phases"]) == {"assembly_s", "force_s", "constraints_s", "solve_s"}        # the drop-in prints the reference's phase lines
     # solution.txt against the shipped golden file (1111 nodes to 16 digits + strain energy 1.061718786130466)
-    u, e = solution_io.read_solution(str(tmp_path / "solution.txt"))
-    u_ref, e_ref = solution_io.read_solution(os.path.join(TREE, "solution.txt"))
-    assert u.shape == u_ref.shape == (1111, 2)
-    assert np.abs(u - u_ref).max() <= 1e-9 * np.abs(u_ref).max()
-    assert abs(e - e_ref) <= 1e-9 * abs(e_ref) and abs(e_ref - 1.061718786130466) < 1e-15
+    u, e, stem = solution_io.read_solution(str(tmp_path / "solution.txt"))
+    u_ref, e_ref, stem_ref = solution_io.read_solution(os.path.join(TREE, "solution.txt"))
+    assert u.shape == u_ref.shape == (2222, 1) and stem == stem_ref == "AMOREBracket"
+    du, de = solution_io.compare(u, e, u_ref, e_ref)
+    assert du <= 1e-9 and de <= 1e-9 and abs(float(e_ref[0, 0]) - 1.061718786130466) < 1e-15
     # SampleData.txt (mofem_b200.sampler on the GPU) against the shipped file: same layout, values to 1e-8 of each component's range
     got, ref = np.loadtxt(tmp_path / "SampleData.txt"), np.loadtxt(os.path.join(TREE, "SampleData.txt"))
     assert got.shape == ref.shape == (57834, 3)
