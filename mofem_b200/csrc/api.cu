@@ -330,11 +330,11 @@ int mofem_assemble(mofem_ctx *ctx)
     CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * 4, s));
     tic(ctx);
     for (int k = 0; k < N_CLASS; k++) {
-        if (k == FAST_CLASS) {      // one launch per (incident elements, triangles) sub-bucket; the last sub-bucket holds no first tasks
-            for (int b = 0; b < N_SUB - 1; b++) {
-                const int64_t n = ctx->cls_count[k * N_SUB + b];
-                if (!n) continue;
-                CK(launch_cell_quads(b / 5 + 1, b % 5 + 1, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB + b], n, ctx->blk_val,
+        if (k == FAST_CLASS) {      // all (incident elements, triangles) sub-buckets in one launch; the last sub-bucket holds no first tasks
+            int64_t any = 0;
+            for (int b = 0; b < N_SUB - 1; b++) any += ctx->cls_count[k * N_SUB + b];
+            if (any) {
+                CK(launch_cell_quads(ctx->P, ctx->T, ctx->cls_tasks, ctx->cls_start + k * N_SUB, ctx->cls_count + k * N_SUB, ctx->blk_val,
                                      ctx->stats, s));
                 ctx->launches[1]++;
             }

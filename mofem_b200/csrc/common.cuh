@@ -74,10 +74,10 @@ cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS
 cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *task_list,
                                    int64_t n_list, double *blk_val, unsigned long long *stats, cudaStream_t s);
 
-// all-quad4 overlay cells with ne incident elements and T straight triangles (first tasks in `first_task`): one evaluation per
-// (point, element), blocks contracted out of shared memory
-cudaError_t launch_cell_quads(int ne, int T, const DevProblem &p, const DevTasks &t, const int32_t *first_task, int64_t n_cells,
-                              double *blk_val, unsigned long long *stats, cudaStream_t s);
+// all-quad4 overlay cells with 1..3 incident elements and 1..5 straight triangles (class FAST_CLASS; sub_start / sub_count: its N_SUB
+// sub-buckets inside cls_tasks): one evaluation per (point, element), blocks contracted out of shared memory, one launch
+cudaError_t launch_cell_quads(const DevProblem &p, const DevTasks &t, const int32_t *cls_tasks, const int64_t *sub_start,
+                              const int64_t *sub_count, double *blk_val, unsigned long long *stats, cudaStream_t s);
 
 // csr.cu
 struct DevCsr {

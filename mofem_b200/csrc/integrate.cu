@@ -427,63 +427,84 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
 // The reference evaluates the strain matrix of element j at every point once for the diagonal block (j,j) and again for every
 // off-diagonal block it takes part in (AMORE.py:59-123): NE evaluations per (point, element).  The values are identical, so here
 // each (point, element) pair is evaluated ONCE.  A CTA takes a batch of CB cells and runs three phases over shared memory:
-//   phase 0  thread per (cell, element): node coordinates -> smem; thread per (cell, triangle, element): det J of the triangle
-//            and grad(rho_e) (constant on a straight triangle) -> smem.
+//   phase 0  thread per (cell, element): node coordinates -> smem; thread per (cell, triangle, element): triangle corners,
+//            det J, rho_e at the corners and grad(rho_e) (constant on a straight triangle) -> smem.
 //   phase 1  thread per EVALUATION (cell, point, element): position, rho, Newton inverse map, shape gradients, the compressed
-//            strain pair (gx[4], gy[4]) -> one 64-byte row in smem.  Short dependent chains at a register count that allows
-//            24 warps per SM: this is where the fp64 pipe is kept busy.
-//   phase 2  two threads per BLOCK (diag j | off (j,l)), each owning two row nodes = 32 of the block's 64 sums: they walk the
+//            strain pair (gx[4], gy[4]) -> one row of 8 doubles in smem.  Short dependent chains at a register count that
+//            allows 24-32 warps per SM: this is where the fp64 pipe is kept busy.
+//   phase 2  four threads per BLOCK (diag j | off (j,l)), each owning one row node = 16 of the block's 64 sums: they walk the
 //            points IN ORDER and accumulate with the same fma sequence as k_amore, reading the rows of elements j and l from
-//            smem, then apply D and store the 2x2 sub-blocks.  Results are bit-identical to the thread-per-block kernel.
-// Cell rows are padded by 16 bytes so that the lanes of different cells hit different banks.
+//            smem, then apply D and store the 2x2 sub-blocks (128 contiguous bytes per thread).  Results are bit-identical to
+//            the thread-per-block kernel.
+// Strain-pair records are 10 doubles apart (8 used; 128-bit stores of a quarter warp cover all 32 banks) and the per-cell stride
+// is 4 mod 16 doubles, so the records of neighbouring cells start in different banks.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int CQ_THREADS = 256;
+#ifndef CQ_THREADS
+#define CQ_THREADS 32                         // one warp per CTA: __syncthreads costs nothing and the ~20 resident CTAs of an SM are in different phases
+#endif
+#ifndef CQ_MINB
+#define CQ_MINB 20                            // resident CTAs per SM the kernel is compiled for (register cap 65536 / CQ_THREADS / CQ_MINB)
+#endif
 constexpr int CQ_MAX_T = 5;                   // triangles per cell handled here (sub-bucket = (NE - 1) * 5 + T - 1)
-constexpr int CQ_SMEM_BUDGET = 72 * 1024;     // per CTA: 3 CTAs per SM
+constexpr int CQ_SMEM_BUDGET = (227 * 1024) / CQ_MINB - 1024 - 256;   // dynamic bytes per CTA
 
-__host__ __device__ inline int cq_row_stride(int ne, int T) { return ne * T * 6 * 8 + 2; }   // doubles per cell in `rows`
-__host__ __device__ inline int cq_cell_doubles(int ne, int T)
-{   // rows + detJ[T] + drho[T][ne][2] + exy[ne][8] + meta (ne + 3 ints, rounded up to doubles)
-    return cq_row_stride(ne, T) + T + T * ne * 2 + ne * 8 + (2 * ne + 3 + 1) / 2;
+constexpr int CQ_ROW = 10;                    // doubles between two strain-pair records: 8 quarter-warp lanes x 16 bytes at this stride cover all 32 banks
+struct CqLayout {       // offsets in doubles inside one cell record
+    int rows, tri, trie, exy, meta, stride;
+};
+__host__ __device__ inline CqLayout cq_layout(int ne, int T)
+{
+    CqLayout L;
+    L.rows = 0;                                  // [T*6][ne][10] gx[4] gy[4] . .   (16-byte aligned records, 128-bit accesses)
+    L.exy = L.rows + ne * T * 6 * CQ_ROW;        // [ne][10]      X[4] Y[4] . .
+    L.tri = L.exy + ne * CQ_ROW;                 // [T][7]        tx[3] ty[3] detJ
+    L.trie = L.tri + T * 7;                      // [T][ne][5]    rho[3] drho_x drho_y
+    L.meta = L.trie + T * ne * 5;                // ints: k0, tri0 lo, tri0 hi, elem[ne], slot[ne]
+    int n = L.meta + (2 * ne + 3 + 1) / 2;
+    L.stride = n + ((4 - n % 16) + 16) % 16;     // stride = 4 mod 16
+    return L;
 }
 
+// one (incident elements, triangles) sub-bucket inside the launch: its CTAs are [cta_start, next cta_start)
+struct CqBucket { int64_t list_off, n_cells; int32_t cta_start, ne, T, CB; };
+struct CqPlan { int32_t n, n_cta; CqBucket b[N_SUB - 1]; };
+
 template <int NE>
-__global__ void __launch_bounds__(CQ_THREADS, 3)
-k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n_cells, int T, int CB,
-             double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
+__device__ __forceinline__ void
+cq_body(const DevProblem &p, const DevTasks &t, const int32_t *__restrict__ first_task, const int64_t n_cells, const int T, const int CB,
+        const int cta, double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
 {
     extern __shared__ double sm[];
     constexpr int TPC = NE * (NE + 1) / 2;                 // blocks (tasks) per cell
     const int EPC = NE * T * 6;                            // evaluations per cell
-    const int RS = cq_row_stride(NE, T);
-    double *rows = sm;                                     // [CB][RS]
-    double *detj = rows + (size_t)CB * RS;                 // [CB][T]
-    double *drho = detj + CB * T;                          // [CB][T][NE][2]
-    double *exy = drho + CB * T * NE * 2;                  // [CB][NE][8]   X[4] Y[4]
-    int32_t *meta = reinterpret_cast<int32_t *>(exy + CB * NE * 8);   // [CB][2 NE + 3]: k0, tri0 (lo, hi), elem[NE], slot[NE]
-    constexpr int MS = 2 * NE + 3;
+    const CqLayout L = cq_layout(NE, T);
+    double *rule = sm;                                     // the 6-point rule: L1[6] L2[6] (thread-dependent index: not from __constant__)
+    double *cells = sm + 12;                               // 16-byte aligned (dynamic shared memory starts 16-byte aligned, 96 bytes in)
     const int tid = threadIdx.x;
-    const int64_t c0 = (int64_t)blockIdx.x * CB;
+    const int64_t c0 = (int64_t)cta * CB;
     const int nb = (int)(n_cells - c0 < CB ? n_cells - c0 : CB);
     const int M = p.n_mesh;
+    const int qoff = tri_rule_offset(6);
     unsigned long long newton = 0, evals = 0;
     bool fail = false;
 
     // ---- phase 0a: per cell -> first task, first triangle, element ids, mesh slots; per (cell, element) -> node coordinates
+    if (tid < 6) { rule[tid] = c_tp[3 * (qoff + tid)]; rule[6 + tid] = c_tp[3 * (qoff + tid) + 1]; }
     for (int i = tid; i < nb * NE; i += CQ_THREADS) {
         const int ci = i / NE, e = i - ci * NE;
         const int64_t k0 = first_task[c0 + ci];
         // the diagonal task of element e inside the cell's task run: (0) | (0, 2) | (0, 3, 5)
         const int dt = (NE == 1) ? 0 : (NE == 2) ? 2 * e : (e == 0 ? 0 : e == 1 ? 3 : 5);
         const int el = t.e1[k0 + dt];
-        int32_t *m = meta + ci * MS;
+        double *cell = cells + (size_t)ci * L.stride;
+        int32_t *m = reinterpret_cast<int32_t *>(cell + L.meta);
         if (e == 0) {
             const int64_t tr0 = p.cell_tri_ptr[t.cell[k0]];
             m[0] = (int32_t)k0; m[1] = (int32_t)(tr0 & 0xffffffffll); m[2] = (int32_t)(tr0 >> 32);
         }
         m[3 + e] = el;
         m[3 + NE + e] = t.slots[k0 + dt] & 0xff;
-        double *xy = exy + (ci * NE + e) * 8;
+        double *xy = cell + L.exy + e * CQ_ROW;
         const int32_t *en = p.elem_nodes + (int64_t)el * 9;
 #pragma unroll
         for (int a = 0; a < 4; a++) {
@@ -492,98 +513,99 @@ k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, i
         }
     }
     __syncthreads();
-    // ---- phase 0b: per (cell, triangle, element) -> det J, grad(rho_e)
+    // ---- phase 0b: per (cell, triangle, element) -> corners, det J, rho_e, grad(rho_e)
     for (int i = tid; i < nb * T * NE; i += CQ_THREADS) {
         const int ci = i / (T * NE), r = i - ci * (T * NE), tr = r / NE, e = r - tr * NE;
-        const int32_t *m = meta + ci * MS;
+        double *cell = cells + (size_t)ci * L.stride;
+        const int32_t *m = reinterpret_cast<const int32_t *>(cell + L.meta);
         const int64_t trg = (((int64_t)m[2] << 32) | (uint32_t)m[1]) + tr;
         const int slot = m[3 + NE + e];
         double tx[3], ty[3], rho[3];
 #pragma unroll
         for (int v = 0; v < 3; v++) {
-            tx[v] = p.tri_xy[6 * trg + 2 * v]; ty[v] = p.tri_xy[6 * trg + 2 * v + 1];
+            const double2 c2 = *reinterpret_cast<const double2 *>(p.tri_xy + 6 * trg + 2 * v);
+            tx[v] = c2.x; ty[v] = c2.y;
             rho[v] = p.tri_rho[(3 * trg + v) * M + slot];
         }
         TriPoint tp;
         tri_straight(tx, ty, tp);
         double gx, gy;
         tri_grad_rho(tp, rho, gx, gy);
-        if (e == 0) detj[ci * T + tr] = tp.detJ;
-        drho[((ci * T + tr) * NE + e) * 2] = gx;
-        drho[((ci * T + tr) * NE + e) * 2 + 1] = gy;
+        if (e == 0) {
+            double *tg = cell + L.tri + tr * 7;
+#pragma unroll
+            for (int v = 0; v < 3; v++) { tg[v] = tx[v]; tg[3 + v] = ty[v]; }
+            tg[6] = tp.detJ;
+        }
+        double *te = cell + L.trie + (tr * NE + e) * 5;
+        te[0] = rho[0]; te[1] = rho[1]; te[2] = rho[2]; te[3] = gx; te[4] = gy;
     }
     __syncthreads();
     // ---- phase 1: one evaluation per (cell, point, element)
-    const int qoff = tri_rule_offset(6);
     for (int ev = tid; ev < nb * EPC; ev += CQ_THREADS) {
         const int ci = ev / EPC, rem = ev - ci * EPC, q = rem / NE, e = rem - q * NE, tr = q / 6, kq = q - tr * 6;
-        const int32_t *m = meta + ci * MS;
-        const int64_t trg = (((int64_t)m[2] << 32) | (uint32_t)m[1]) + tr;
-        const int slot = m[3 + NE + e];
-        double tx[3], ty[3], rho[3];
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
-            tx[v] = p.tri_xy[6 * trg + 2 * v]; ty[v] = p.tri_xy[6 * trg + 2 * v + 1];
-            rho[v] = p.tri_rho[(3 * trg + v) * M + slot];
-        }
-        const double L1 = c_tp[3 * (qoff + kq)], L2 = c_tp[3 * (qoff + kq) + 1];
-        double Nt[3] = {L1, L2, 1.0 - L1 - L2};
+        double *cell = cells + (size_t)ci * L.stride;
+        const double *tg = cell + L.tri + tr * 7;
+        const double *te = cell + L.trie + (tr * NE + e) * 5;
+        const double2 *xy = reinterpret_cast<const double2 *>(cell + L.exy + e * CQ_ROW);
+        const double tx[3] = {tg[0], tg[1], tg[2]}, ty[3] = {tg[3], tg[4], tg[5]}, rho[3] = {te[0], te[1], te[2]};
+        const double L1 = rule[kq], L2 = rule[6 + kq];
+        const double Nt[3] = {L1, L2, 1.0 - L1 - L2};
         const double x = dot_vecmat<3>(Nt, tx), y = dot_vecmat<3>(Nt, ty);
         const double rv = dot_gemm<3>(Nt, rho);
-        const double *dr = drho + ((ci * T + tr) * NE + e) * 2;
-        const double *xy = exy + (ci * NE + e) * 8;
-        double X[4], Y[4], gx[4], gy[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) { X[a] = xy[a]; Y[a] = xy[4 + a]; }
-        const int it = strain_pair<4>(X, Y, x, y, rv, dr[0], dr[1], gx, gy);
-        if (it < 0) fail = true; else newton += (unsigned long long)it * NE;     // the reference evaluates NE times (1 diag + NE-1 off)
+        double gx[4], gy[4];
+        const double2 x01 = xy[0], x23 = xy[1], y01 = xy[2], y23 = xy[3];
+        const double X[4] = {x01.x, x01.y, x23.x, x23.y}, Y[4] = {y01.x, y01.y, y23.x, y23.y};
+        const int it = strain_pair<4>(X, Y, x, y, rv, te[3], te[4], gx, gy);
+        if (it < 0) fail = true; else newton += (unsigned long long)(it * NE);   // the reference evaluates NE times (1 diag + NE-1 off)
         evals += NE;
-        double2 *row = reinterpret_cast<double2 *>(rows + (size_t)ci * RS + (q * NE + e) * 8);
+        double2 *row = reinterpret_cast<double2 *>(cell + L.rows + (q * NE + e) * CQ_ROW);
         row[0] = make_double2(gx[0], gx[1]); row[1] = make_double2(gx[2], gx[3]);
         row[2] = make_double2(gy[0], gy[1]); row[3] = make_double2(gy[2], gy[3]);
     }
     __syncthreads();
-    // ---- phase 2: two threads per block, 2 row nodes x 4 column nodes x 4 sums each
-    if (tid < nb * TPC * 2) {
-        const int ci = tid / (TPC * 2), r = tid - ci * (TPC * 2), tk = r >> 1, h = r & 1;
+    // ---- phase 2: four threads per block, one row node x 4 column nodes x 4 sums each
+    for (int item = tid; item < nb * TPC * 4; item += CQ_THREADS) {
+        const int ci = item / (TPC * 4), r = item - ci * (TPC * 4), tk = r >> 2, a = r & 3;
         int ej, el;
         if (NE == 1) { ej = 0; el = 0; }
         else if (NE == 2) { ej = tk == 2 ? 1 : 0; el = tk == 0 ? 0 : 1; }
         else { ej = tk < 3 ? 0 : (tk < 5 ? 1 : 2); el = tk < 3 ? tk : (tk < 5 ? tk - 2 : 2); }
-        const double *base = rows + (size_t)ci * RS;
-        double S[32];
+        const double *cell = cells + (size_t)ci * L.stride;
+        const double *r1 = cell + L.rows + ej * CQ_ROW + a;
+        const double2 *r2 = reinterpret_cast<const double2 *>(cell + L.rows + el * CQ_ROW);
+        const double *tg = cell + L.tri + 6;
+        double S[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) S[i] = 0.0;
-        const int npt = T * 6;
-        for (int q = 0; q < npt; q++) {
-            const int tr = q / 6, kq = q - tr * 6;
-            const double w = 0.5 * detj[ci * T + tr] * c_tw[qoff + kq];
-            const double2 *r1 = reinterpret_cast<const double2 *>(base + (q * NE + ej) * 8);
-            const double2 *r2 = reinterpret_cast<const double2 *>(base + (q * NE + el) * 8);
-            const double2 a_x = r1[h], a_y = r1[2 + h];                  // g1x, g1y of row nodes 2h, 2h+1
-            const double2 b0 = r2[0], b1 = r2[1], b2 = r2[2], b3 = r2[3];
-            const double g2x[4] = {b0.x, b0.y, b1.x, b1.y}, g2y[4] = {b2.x, b2.y, b3.x, b3.y};
-            const double wx[2] = {w * a_x.x, w * a_x.y}, wy[2] = {w * a_y.x, w * a_y.y};
+        for (int i = 0; i < 16; i++) S[i] = 0.0;
+        for (int tr = 0; tr < T; tr++) {
+            const double hd = 0.5 * tg[tr * 7];
 #pragma unroll
-            for (int a = 0; a < 2; a++)
+            for (int kq = 0; kq < 6; kq++) {
+                const double w = hd * c_tw[qoff + kq];
+                const double wx = w * r1[0], wy = w * r1[4];
+                const double2 b0 = r2[0], b1 = r2[1], b2 = r2[2], b3 = r2[3];
+                const double gbx[4] = {b0.x, b0.y, b1.x, b1.y}, gby[4] = {b2.x, b2.y, b3.x, b3.y};
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    double *s4 = S + 4 * (a * 4 + b);
-                    s4[0] = fma(wx[a], g2x[b], s4[0]);
-                    s4[1] = fma(wx[a], g2y[b], s4[1]);
-                    s4[2] = fma(wy[a], g2x[b], s4[2]);
-                    s4[3] = fma(wy[a], g2y[b], s4[3]);
+                    const double g2x = gbx[b], g2y = gby[b];
+                    S[4 * b + 0] = fma(wx, g2x, S[4 * b + 0]);
+                    S[4 * b + 1] = fma(wx, g2y, S[4 * b + 1]);
+                    S[4 * b + 2] = fma(wy, g2x, S[4 * b + 2]);
+                    S[4 * b + 3] = fma(wy, g2y, S[4 * b + 3]);
                 }
+                r1 += NE * CQ_ROW; r2 += NE * (CQ_ROW / 2);
+            }
         }
-        const int32_t *m = meta + ci * MS;
+        const int32_t *m = reinterpret_cast<const int32_t *>(cell + L.meta);
         // diag j and off (j,l) use element j's material (AMORE.py:113)
         const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[m[3 + ej]];
         double D[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
-        double *out = blk_val + 4 * (t.pair_off[(int64_t)m[0] + tk] + 8 * h);
+        double *out = blk_val + 4 * (t.pair_off[(int64_t)m[0] + tk] + 4 * a);
 #pragma unroll
-        for (int ab = 0; ab < 8; ab++) store_pair(out + 4 * ab, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
+        for (int b = 0; b < 4; b++) store_pair(out + 4 * b, D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3]);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -597,32 +619,66 @@ k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, i
     if (fail) stats[2] = 1;
 }
 
-template <int NE>
-static cudaError_t launch_cell_quads_ne(int T, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
-                                        double *blk_val, unsigned long long *stats, cudaStream_t s)
+// All sub-buckets in ONE launch (the tails of the small sub-buckets overlap the big ones): a CTA looks its sub-bucket up in the plan.
+__global__ void __launch_bounds__(CQ_THREADS, CQ_MINB)
+k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ cls_tasks, CqPlan plan, double *__restrict__ blk_val,
+             unsigned long long *__restrict__ stats)
 {
-    constexpr int TPC = NE * (NE + 1) / 2;
-    const int per_cell = cq_cell_doubles(NE, T) * 8;
-    int CB = CQ_THREADS / 2 / TPC;
-    if (CB > CQ_SMEM_BUDGET / per_cell) CB = CQ_SMEM_BUDGET / per_cell;
-    if (CB < 1) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)CB * per_cell + 64;
-    cudaError_t e = cudaFuncSetAttribute(k_cell_quads<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_SMEM_BUDGET + 64);
-    if (e != cudaSuccess) return e;
-    k_cell_quads<NE><<<(unsigned)((n + CB - 1) / CB), CQ_THREADS, smem, s>>>(p, t, list, n, T, CB, blk_val, stats);
-    return cudaGetLastError();
+    int i = 0;
+    while (i + 1 < plan.n && (int)blockIdx.x >= plan.b[i + 1].cta_start) i++;
+    const CqBucket &b = plan.b[i];
+    const int cta = (int)blockIdx.x - b.cta_start;
+    switch (b.ne) {
+    case 1: cq_body<1>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    case 2: cq_body<2>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    default: cq_body<3>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    }
 }
 
-cudaError_t launch_cell_quads(int ne, int T, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
-                              double *blk_val, unsigned long long *stats, cudaStream_t s)
+// cells per CTA: the largest batch inside the shared-memory budget whose evaluations (phase 1, ~70 % of the work) and block rows
+// (phase 2) fill whole rounds of CQ_THREADS threads best
+static int cq_batch(int ne, int T)
 {
-    if (n == 0) return cudaSuccess;
-    switch (ne) {
-    case 1: return launch_cell_quads_ne<1>(T, p, t, list, n, blk_val, stats, s);
-    case 2: return launch_cell_quads_ne<2>(T, p, t, list, n, blk_val, stats, s);
-    case 3: return launch_cell_quads_ne<3>(T, p, t, list, n, blk_val, stats, s);
-    default: return cudaErrorInvalidValue;
+    const int tpc = ne * (ne + 1) / 2, epc = ne * T * 6;
+    const int cbmax = (CQ_SMEM_BUDGET - 12 * 8) / (cq_layout(ne, T).stride * 8);
+    int best = 0;
+    double best_eff = -1.0;
+    for (int cb = 1; cb <= cbmax; cb++) {
+        const int e1 = cb * epc, e2 = cb * tpc * 4;
+        const double f1 = (double)e1 / (((e1 + CQ_THREADS - 1) / CQ_THREADS) * CQ_THREADS);
+        const double f2 = (double)e2 / (((e2 + CQ_THREADS - 1) / CQ_THREADS) * CQ_THREADS);
+        const double eff = 0.7 * f1 + 0.3 * f2;
+        if (eff >= best_eff - 1e-9 && (eff > best_eff + 0.01 || cb > best)) { if (eff > best_eff) best_eff = eff; best = cb; }
     }
+    return best;
+}
+
+// sub_start / sub_count: the N_SUB sub-buckets of class FAST_CLASS inside cls_tasks; sub-bucket (ne - 1) * 5 + T - 1 holds the first
+// tasks of the cells with ne incident quads and T triangles (the last sub-bucket, their other tasks, is not iterated)
+cudaError_t launch_cell_quads(const DevProblem &p, const DevTasks &t, const int32_t *cls_tasks, const int64_t *sub_start,
+                              const int64_t *sub_count, double *blk_val, unsigned long long *stats, cudaStream_t s)
+{
+    CqPlan plan{};
+    size_t smem = 0;
+    int64_t n_cta = 0;
+    for (int sb = N_SUB - 2; sb >= 0; sb--) {         // heaviest CTAs first: 3 elements before 2 before 1, many triangles before few
+        if (!sub_count[sb]) continue;
+        const int ne = sb / CQ_MAX_T + 1, T = sb % CQ_MAX_T + 1;
+        const int CB = cq_batch(ne, T);
+        if (CB < 1) return cudaErrorInvalidValue;
+        CqBucket &b = plan.b[plan.n++];
+        b.list_off = sub_start[sb]; b.n_cells = sub_count[sb]; b.cta_start = (int32_t)n_cta; b.ne = ne; b.T = T; b.CB = CB;
+        n_cta += (sub_count[sb] + CB - 1) / CB;
+        const size_t need = (size_t)CB * cq_layout(ne, T).stride * 8 + 12 * 8;
+        if (need > smem) smem = need;
+    }
+    if (!plan.n) return cudaSuccess;
+    if (n_cta > 0x7fffffff) return cudaErrorInvalidValue;
+    plan.n_cta = (int32_t)n_cta;
+    cudaError_t e = cudaFuncSetAttribute(k_cell_quads, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_SMEM_BUDGET);
+    if (e != cudaSuccess) return e;
+    k_cell_quads<<<(unsigned)n_cta, CQ_THREADS, smem, s>>>(p, t, cls_tasks, plan, blk_val, stats);
+    return cudaGetLastError();
 }
 
 // Regular elements: triFE (1 pt) / triQuadFE (3 pts) / quadFE (2x2) / quadQuadFE (3x3), stiffnessMatrix.py:9-81.
