@@ -18,6 +18,7 @@ struct mofem_ctx {
     // tasks
     DevTasks T{};
     int32_t *cls_tasks = nullptr;
+    CqRec *cq_rec = nullptr;   // records of the cell kernel's cells (class FAST_CLASS), sub-bucket order
     int64_t cls_count[N_BUCKET]{}, cls_start[N_BUCKET]{};
     int64_t n_pair = 0, n_coo = 0;
     std::vector<void *> sym_allocs;
@@ -271,6 +272,15 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(cudaMemcpyAsync(cls_start_d, ctx->cls_start, sizeof(int64_t) * N_BUCKET, cudaMemcpyHostToDevice, s));
     CKT(cudaMemsetAsync(cls_count_d, 0, sizeof(int64_t) * N_BUCKET, s));
     CKT(launch_bucket_tasks(T, cls_count_d, cls_start_d, ctx->cls_tasks, 1, s)); L++;
+    {   // records of the cell kernel: the first tasks of its cells are sub-buckets 0 .. N_SUB-2 of class FAST_CLASS, contiguous in cls_tasks
+        int64_t n_fast = 0;
+        for (int b = 0; b < N_SUB - 1; b++) n_fast += ctx->cls_count[FAST_CLASS * N_SUB + b];
+        ctx->cq_rec = nullptr;
+        if (n_fast) {
+            if ((rc = dev_alloc(ctx, &ctx->cq_rec, n_fast, pool))) { cleanup(); return rc; }
+            CKT(launch_cq_records(P, T, ctx->cls_tasks + ctx->cls_start[FAST_CLASS * N_SUB], n_fast, ctx->cq_rec, s)); L++;
+        }
+    }
     // --- CSR symbolic ---------------------------------------------------------------------
     DevCsr &C = ctx->C;
     C.n_node = P.n_node;
@@ -334,8 +344,7 @@ int mofem_assemble(mofem_ctx *ctx)
             int64_t any = 0;
             for (int b = 0; b < N_SUB - 1; b++) any += ctx->cls_count[k * N_SUB + b];
             if (any) {
-                CK(launch_cell_quads(ctx->P, ctx->T, ctx->cls_tasks, ctx->cls_start + k * N_SUB, ctx->cls_count + k * N_SUB, ctx->blk_val,
-                                     ctx->stats, s));
+                CK(launch_cell_quads(ctx->P, ctx->cq_rec, ctx->cls_count + k * N_SUB, ctx->blk_val, ctx->stats, s));
                 ctx->launches[1]++;
             }
             continue;

@@ -74,10 +74,17 @@ cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS
 cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *task_list,
                                    int64_t n_list, double *blk_val, unsigned long long *stats, cudaStream_t s);
 
-// all-quad4 overlay cells with 1..3 incident elements and 1..5 straight triangles (class FAST_CLASS; sub_start / sub_count: its N_SUB
-// sub-buckets inside cls_tasks): one evaluation per (point, element), blocks contracted out of shared memory, one launch
-cudaError_t launch_cell_quads(const DevProblem &p, const DevTasks &t, const int32_t *cls_tasks, const int64_t *sub_start,
-                              const int64_t *sub_count, double *blk_val, unsigned long long *stats, cudaStream_t s);
+// all-quad4 overlay cells with 1..3 incident elements and 1..5 straight triangles (class FAST_CLASS): one evaluation per
+// (point, element), blocks contracted out of shared memory, one launch.  Symbolic phase: one record per cell in sub-bucket order.
+struct alignas(32) CqRec {
+    int64_t pair0;     // offset of the cell's first block in blk_val (node pairs); its blocks follow each other, 16 pairs each
+    int64_t tri0;      // first integration triangle
+    int32_t el[3];     // incident elements in mesh order
+    int32_t slots;     // their mesh slots, 8 bits each
+};
+cudaError_t launch_cq_records(const DevProblem &p, const DevTasks &t, const int32_t *first_task, int64_t n, CqRec *rec, cudaStream_t s);
+cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count /*[N_SUB]*/, double *blk_val,
+                              unsigned long long *stats, cudaStream_t s);
 
 // csr.cu
 struct DevCsr {

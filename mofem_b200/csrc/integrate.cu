@@ -16,6 +16,7 @@
 //   [K(2a,2b), K(2a,2b+1), K(2a+1,2b), K(2a+1,2b+1)]   (one 32-byte sector per node pair).
 //
 // Compiled with -fmad=false (see fem_device.cuh); accumulations use explicit fma().
+#include <cstdlib>
 #include "common.cuh"
 #include "fem_device.cuh"
 
@@ -450,7 +451,7 @@ constexpr int CQ_SMEM_BUDGET = (227 * 1024) / CQ_MINB - 1024 - 256;   // dynamic
 
 constexpr int CQ_ROW = 10;                    // doubles between two strain-pair records: 8 quarter-warp lanes x 16 bytes at this stride cover all 32 banks
 struct CqLayout {       // offsets in doubles inside one cell record
-    int rows, tri, trie, exy, meta, stride;
+    int rows, exy, tri, trie, meta, stride;
 };
 __host__ __device__ inline CqLayout cq_layout(int ne, int T)
 {
@@ -459,8 +460,8 @@ __host__ __device__ inline CqLayout cq_layout(int ne, int T)
     L.exy = L.rows + ne * T * 6 * CQ_ROW;        // [ne][10]      X[4] Y[4] . .
     L.tri = L.exy + ne * CQ_ROW;                 // [T][7]        tx[3] ty[3] detJ
     L.trie = L.tri + T * 7;                      // [T][ne][5]    rho[3] drho_x drho_y
-    L.meta = L.trie + T * ne * 5;                // ints: k0, tri0 lo, tri0 hi, elem[ne], slot[ne]
-    int n = L.meta + (2 * ne + 3 + 1) / 2;
+    L.meta = L.trie + T * ne * 5;                // int64: offset of the cell's first block in blk_val (node pairs); int32[ne]: material ids
+    int n = L.meta + 1 + (ne + 1) / 2;
     L.stride = n + ((4 - n % 16) + 16) % 16;     // stride = 4 mod 16
     return L;
 }
@@ -469,10 +470,37 @@ __host__ __device__ inline CqLayout cq_layout(int ne, int T)
 struct CqBucket { int64_t list_off, n_cells; int32_t cta_start, ne, T, CB; };
 struct CqPlan { int32_t n, n_cta; CqBucket b[N_SUB - 1]; };
 
+// Symbolic phase: one 32-byte record per cell of the cell kernel, in the order of the sub-bucket lists, so that the kernel reaches
+// its inputs in three dependent loads (record -> element nodes / material id -> coordinates / D) instead of five.
+__global__ void k_cq_records(DevProblem p, DevTasks t, const int32_t *__restrict__ first_task, int64_t n, CqRec *__restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k0 = first_task[i];
+    const int64_t c = t.cell[k0];
+    const int32_t *ce = p.cell_elem + c * p.n_mesh;
+    CqRec r;
+    r.pair0 = t.pair_off[k0];
+    r.tri0 = p.cell_tri_ptr[c];
+    r.el[0] = r.el[1] = r.el[2] = -1;
+    r.slots = 0;
+    int e = 0;
+    for (int j = 0; j < p.n_mesh && e < 3; j++)
+        if (ce[j] >= 0) { r.el[e] = ce[j]; r.slots |= j << (8 * e); e++; }
+    rec[i] = r;
+}
+
+cudaError_t launch_cq_records(const DevProblem &p, const DevTasks &t, const int32_t *first_task, int64_t n, CqRec *rec, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    k_cq_records<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, t, first_task, n, rec);
+    return cudaGetLastError();
+}
+
 template <int NE>
 __device__ __forceinline__ void
-cq_body(const DevProblem &p, const DevTasks &t, const int32_t *__restrict__ first_task, const int64_t n_cells, const int T, const int CB,
-        const int cta, double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
+cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cells, const int T, const int CB, const int cta,
+        double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
 {
     extern __shared__ double sm[];
     constexpr int TPC = NE * (NE + 1) / 2;                 // blocks (tasks) per cell
@@ -488,44 +516,42 @@ cq_body(const DevProblem &p, const DevTasks &t, const int32_t *__restrict__ firs
     unsigned long long newton = 0, evals = 0;
     bool fail = false;
 
-    // ---- phase 0a: per cell -> first task, first triangle, element ids, mesh slots; per (cell, element) -> node coordinates
+    // ---- phase 0: thread per (cell, triangle, element) -> corners, det J, rho_e, grad(rho_e); the thread of triangle 0 also
+    //      fetches the element: node coordinates and material id.  All loads hang off the cell record.
     if (tid < 6) { rule[tid] = c_tp[3 * (qoff + tid)]; rule[6 + tid] = c_tp[3 * (qoff + tid) + 1]; }
-    for (int i = tid; i < nb * NE; i += CQ_THREADS) {
-        const int ci = i / NE, e = i - ci * NE;
-        const int64_t k0 = first_task[c0 + ci];
-        // the diagonal task of element e inside the cell's task run: (0) | (0, 2) | (0, 3, 5)
-        const int dt = (NE == 1) ? 0 : (NE == 2) ? 2 * e : (e == 0 ? 0 : e == 1 ? 3 : 5);
-        const int el = t.e1[k0 + dt];
-        double *cell = cells + (size_t)ci * L.stride;
-        int32_t *m = reinterpret_cast<int32_t *>(cell + L.meta);
-        if (e == 0) {
-            const int64_t tr0 = p.cell_tri_ptr[t.cell[k0]];
-            m[0] = (int32_t)k0; m[1] = (int32_t)(tr0 & 0xffffffffll); m[2] = (int32_t)(tr0 >> 32);
-        }
-        m[3 + e] = el;
-        m[3 + NE + e] = t.slots[k0 + dt] & 0xff;
-        double *xy = cell + L.exy + e * CQ_ROW;
-        const int32_t *en = p.elem_nodes + (int64_t)el * 9;
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const double2 v = *reinterpret_cast<const double2 *>(p.node_xy + 2 * (int64_t)en[a]);
-            xy[a] = v.x; xy[4 + a] = v.y;
-        }
-    }
-    __syncthreads();
-    // ---- phase 0b: per (cell, triangle, element) -> corners, det J, rho_e, grad(rho_e)
     for (int i = tid; i < nb * T * NE; i += CQ_THREADS) {
         const int ci = i / (T * NE), r = i - ci * (T * NE), tr = r / NE, e = r - tr * NE;
+        const int4 *rp = reinterpret_cast<const int4 *>(recs + c0 + ci);
+        const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);       // pair0 | tri0 ; el[3] | slots
+        const int64_t trg = (((int64_t)r0.w << 32) | (uint32_t)r0.z) + tr;
+        const int el = e == 0 ? r1.x : e == 1 ? r1.y : r1.z;
+        const int slot = (r1.w >> (8 * e)) & 0xff;
         double *cell = cells + (size_t)ci * L.stride;
-        const int32_t *m = reinterpret_cast<const int32_t *>(cell + L.meta);
-        const int64_t trg = (((int64_t)m[2] << 32) | (uint32_t)m[1]) + tr;
-        const int slot = m[3 + NE + e];
+        const bool lead = tr == 0;
+        int en[4] = {0, 0, 0, 0};
+        int mat = 0;
+        if (lead) {
+            const int32_t *enp = p.elem_nodes + (int64_t)el * 9;
+#pragma unroll
+            for (int a = 0; a < 4; a++) en[a] = enp[a];
+            mat = p.elem_mat[el];
+        }
         double tx[3], ty[3], rho[3];
 #pragma unroll
         for (int v = 0; v < 3; v++) {
             const double2 c2 = *reinterpret_cast<const double2 *>(p.tri_xy + 6 * trg + 2 * v);
             tx[v] = c2.x; ty[v] = c2.y;
             rho[v] = p.tri_rho[(3 * trg + v) * M + slot];
+        }
+        if (lead) {
+            double *xy = cell + L.exy + e * CQ_ROW;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const double2 v = *reinterpret_cast<const double2 *>(p.node_xy + 2 * (int64_t)en[a]);
+                xy[a] = v.x; xy[4 + a] = v.y;
+            }
+            reinterpret_cast<int32_t *>(cell + L.meta + 1)[e] = mat;
+            if (e == 0) *reinterpret_cast<int64_t *>(cell + L.meta) = ((int64_t)r0.y << 32) | (uint32_t)r0.x;
         }
         TriPoint tp;
         tri_straight(tx, ty, tp);
@@ -597,13 +623,13 @@ cq_body(const DevProblem &p, const DevTasks &t, const int32_t *__restrict__ firs
                 r1 += NE * CQ_ROW; r2 += NE * (CQ_ROW / 2);
             }
         }
-        const int32_t *m = reinterpret_cast<const int32_t *>(cell + L.meta);
         // diag j and off (j,l) use element j's material (AMORE.py:113)
-        const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[m[3 + ej]];
+        const double *Dp = p.mat_D + 9 * (int64_t)reinterpret_cast<const int32_t *>(cell + L.meta + 1)[ej];
         double D[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
-        double *out = blk_val + 4 * (t.pair_off[(int64_t)m[0] + tk] + 4 * a);
+        // the blocks of a cell are consecutive in blk_val, 16 node pairs each
+        double *out = blk_val + 4 * (*reinterpret_cast<const int64_t *>(cell + L.meta) + 16 * tk + 4 * a);
 #pragma unroll
         for (int b = 0; b < 4; b++) store_pair(out + 4 * b, D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3]);
     }
@@ -621,7 +647,7 @@ cq_body(const DevProblem &p, const DevTasks &t, const int32_t *__restrict__ firs
 
 // All sub-buckets in ONE launch (the tails of the small sub-buckets overlap the big ones): a CTA looks its sub-bucket up in the plan.
 __global__ void __launch_bounds__(CQ_THREADS, CQ_MINB)
-k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ cls_tasks, CqPlan plan, double *__restrict__ blk_val,
+k_cell_quads(DevProblem p, const CqRec *__restrict__ recs, CqPlan plan, double *__restrict__ blk_val,
              unsigned long long *__restrict__ stats)
 {
     int i = 0;
@@ -629,9 +655,9 @@ k_cell_quads(DevProblem p, DevTasks t, const int32_t *__restrict__ cls_tasks, Cq
     const CqBucket &b = plan.b[i];
     const int cta = (int)blockIdx.x - b.cta_start;
     switch (b.ne) {
-    case 1: cq_body<1>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
-    case 2: cq_body<2>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
-    default: cq_body<3>(p, t, cls_tasks + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    case 1: cq_body<1>(p, recs + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    case 2: cq_body<2>(p, recs + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
+    default: cq_body<3>(p, recs + b.list_off, b.n_cells, b.T, b.CB, cta, blk_val, stats); break;
     }
 }
 
@@ -653,18 +679,24 @@ static int cq_batch(int ne, int T)
     return best;
 }
 
-// sub_start / sub_count: the N_SUB sub-buckets of class FAST_CLASS inside cls_tasks; sub-bucket (ne - 1) * 5 + T - 1 holds the first
-// tasks of the cells with ne incident quads and T triangles (the last sub-bucket, their other tasks, is not iterated)
-cudaError_t launch_cell_quads(const DevProblem &p, const DevTasks &t, const int32_t *cls_tasks, const int64_t *sub_start,
-                              const int64_t *sub_count, double *blk_val, unsigned long long *stats, cudaStream_t s)
+// sub_count: cells in the N_SUB sub-buckets of class FAST_CLASS; sub-bucket (ne - 1) * 5 + T - 1 = the cells with ne incident quads
+// and T triangles, whose records follow each other in `recs` in sub-bucket order (the last sub-bucket holds no cells)
+cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count, double *blk_val,
+                              unsigned long long *stats, cudaStream_t s)
 {
     CqPlan plan{};
     size_t smem = 0;
-    int64_t n_cta = 0;
+    int64_t n_cta = 0, sub_start[N_SUB];
+    sub_start[0] = 0;
+    for (int sb = 1; sb < N_SUB; sb++) sub_start[sb] = sub_start[sb - 1] + sub_count[sb - 1];
     for (int sb = N_SUB - 2; sb >= 0; sb--) {         // heaviest CTAs first: 3 elements before 2 before 1, many triangles before few
         if (!sub_count[sb]) continue;
         const int ne = sb / CQ_MAX_T + 1, T = sb % CQ_MAX_T + 1;
-        const int CB = cq_batch(ne, T);
+        int CB = cq_batch(ne, T);
+        if (const char *ov = getenv("MOFEM_CQ_CB")) {      // tuning override: cells per CTA (clamped to the hardware limit)
+            const int lim = (int)((227 * 1024 - 1024 - 96) / (cq_layout(ne, T).stride * 8));
+            CB = atoi(ov) < lim ? atoi(ov) : lim;
+        }
         if (CB < 1) return cudaErrorInvalidValue;
         CqBucket &b = plan.b[plan.n++];
         b.list_off = sub_start[sb]; b.n_cells = sub_count[sb]; b.cta_start = (int32_t)n_cta; b.ne = ne; b.T = T; b.CB = CB;
@@ -675,9 +707,9 @@ cudaError_t launch_cell_quads(const DevProblem &p, const DevTasks &t, const int3
     if (!plan.n) return cudaSuccess;
     if (n_cta > 0x7fffffff) return cudaErrorInvalidValue;
     plan.n_cta = (int32_t)n_cta;
-    cudaError_t e = cudaFuncSetAttribute(k_cell_quads, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(k_cell_quads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > (size_t)CQ_SMEM_BUDGET ? smem : (size_t)CQ_SMEM_BUDGET));
     if (e != cudaSuccess) return e;
-    k_cell_quads<<<(unsigned)n_cta, CQ_THREADS, smem, s>>>(p, t, cls_tasks, plan, blk_val, stats);
+    k_cell_quads<<<(unsigned)n_cta, CQ_THREADS, smem, s>>>(p, recs, plan, blk_val, stats);
     return cudaGetLastError();
 }
 
