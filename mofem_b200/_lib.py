@@ -116,12 +116,29 @@ def raise_for(code, ctx_handle):
     raise MofemError(f"mofem_b200 error {code}: {msg}")
 
 
-def ptr(a):
-    """Raw address of a numpy array or a torch tensor (host or device), or None."""
+_TORCH_NAMES = {"float64": "torch.float64", "int32": "torch.int32", "int64": "torch.int64", "uint8": "torch.uint8"}
+
+
+def ptr(a, dtype=None, device=None, what="array"):
+    """Raw address of a numpy array or a torch tensor (host or device), or None.
+
+    The C-ABI takes plain pointers, so a wrong element type, a strided view or a tensor on another GPU would be reinterpreted
+    silently: with ``dtype`` (a numpy dtype) the array must have exactly that type and be C-contiguous, and a CUDA tensor must
+    live on GPU ``device`` (the context's device) when that is given -- otherwise TypeError / ValueError."""
     if a is None:
         return None
     if isinstance(a, np.ndarray):
+        if dtype is not None and a.dtype != np.dtype(dtype):
+            raise TypeError(f"{what}: expected {np.dtype(dtype).name}, got {a.dtype.name}")
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{what}: array must be C-contiguous")
         return a.ctypes.data
     if hasattr(a, "data_ptr"):
+        if dtype is not None and str(a.dtype) != _TORCH_NAMES.get(np.dtype(dtype).name):
+            raise TypeError(f"{what}: expected {_TORCH_NAMES.get(np.dtype(dtype).name)}, got {a.dtype}")
+        if not a.is_contiguous():
+            raise ValueError(f"{what}: tensor must be contiguous")
+        if device is not None and getattr(a, "is_cuda", False) and a.device.index != device:
+            raise ValueError(f"{what}: tensor is on cuda:{a.device.index}, the context on cuda:{device}")
         return a.data_ptr()
     raise TypeError(type(a))

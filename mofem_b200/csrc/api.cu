@@ -294,6 +294,10 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(exclusive_scan_i32_to_i64(row_cnt, C.row_start, P.n_node, C.row_start + P.n_node, s, &L));
     CKT(cudaMemcpyAsync(&C.n_entry, C.row_start + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
+    if (C.n_entry >= (1ll << 32)) {
+        cleanup();
+        return ctx_fail(ctx, MOFEM_E_LIMIT, "more than 2^32 block contributions on one device: shard the cells over more GPUs");
+    }
     uint64_t *entries;
     if ((rc = dev_alloc(ctx, &entries, C.n_entry, tmp))) { cleanup(); return rc; }
     CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
@@ -317,12 +321,15 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(cudaMemcpyAsync(&C.n_upair, C.node_ptr + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
     if ((rc = dev_alloc(ctx, &C.node_idx, C.n_upair + 8, pool)) || (rc = dev_alloc(ctx, &C.pair_row, C.n_upair, pool)) ||
-        (rc = dev_alloc(ctx, &C.contrib_ptr, C.n_upair + 1, pool)) || (rc = dev_alloc(ctx, &C.contrib_src, C.n_entry, pool)) ||
-        (rc = dev_alloc(ctx, &ctx->data, 4 * C.n_upair, pool)) || (rc = dev_alloc(ctx, &ctx->blk_val, 4 * ctx->n_pair, pool))) {
+        (rc = dev_alloc(ctx, &C.contrib_ptr, C.n_upair + 1, pool)) || (rc = dev_alloc(ctx, &C.pair_dst, 2 * ctx->n_pair, pool)) ||
+        (rc = dev_alloc(ctx, &ctx->data, 4 * C.n_upair, pool)) || (rc = dev_alloc(ctx, &ctx->blk_val, 4 * C.n_entry, pool))) {
         cleanup(); return rc;
     }
-    CKT(csr_emit(P.n_node, C.row_start, entries, C.node_ptr, C.node_idx, C.pair_row, C.contrib_ptr, C.contrib_src, s)); L++;
+    uint32_t *contrib_src;
+    if ((rc = dev_alloc(ctx, &contrib_src, C.n_entry, tmp))) { cleanup(); return rc; }
+    CKT(csr_emit(P.n_node, C.row_start, entries, C.node_ptr, C.node_idx, C.pair_row, C.contrib_ptr, contrib_src, s)); L++;
     CKT(cudaMemcpyAsync(C.contrib_ptr + C.n_upair, &C.n_entry, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    CKT(csr_pair_dst(C, contrib_src, ctx->n_pair, s)); L++;
     ctx->ms[0] = toc(ctx);
     CKT(cudaGetLastError());
     cleanup();
@@ -339,12 +346,13 @@ int mofem_assemble(mofem_ctx *ctx)
     ctx->launches[1] = ctx->launches[2] = 0;
     CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * 4, s));
     tic(ctx);
+    const BlkOut out{ctx->blk_val, ctx->C.pair_dst, ctx->n_pair};   // records in reduction order, addressed through the inverse map
     for (int k = 0; k < N_CLASS; k++) {
         if (k == FAST_CLASS) {      // all (incident elements, triangles) sub-buckets in one launch; the last sub-bucket holds no first tasks
             int64_t any = 0;
             for (int b = 0; b < N_SUB - 1; b++) any += ctx->cls_count[k * N_SUB + b];
             if (any) {
-                CK(launch_cell_quads(ctx->P, ctx->cq_rec, ctx->cls_count + k * N_SUB, ctx->blk_val, ctx->stats, s));
+                CK(launch_cell_quads(ctx->P, ctx->cq_rec, ctx->cls_count + k * N_SUB, out, ctx->stats, s));
                 ctx->launches[1]++;
             }
             continue;
@@ -352,7 +360,7 @@ int mofem_assemble(mofem_ctx *ctx)
         int64_t n_cls = 0;
         for (int b = 0; b < N_SUB; b++) n_cls += ctx->cls_count[k * N_SUB + b];
         if (!n_cls) continue;
-        CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB], n_cls, ctx->blk_val,
+        CK(launch_integrate_class(k, ctx->P, ctx->T, ctx->cls_tasks + ctx->cls_start[k * N_SUB], n_cls, out,
                                   ctx->stats, s));
         ctx->launches[1]++;
     }
@@ -414,8 +422,10 @@ int mofem_get_coo_values(mofem_ctx *ctx, double *V)
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int64_t nt = ctx->T.n_task;
-    // pure re-layout (no arithmetic) of blk_val into the reference's emission order, done on the host
-    std::vector<double> blk((size_t)(4 * ctx->n_pair));
+    // pure re-layout (no arithmetic) of blk_val (reduction order) into the reference's emission order, done on the host
+    std::vector<double> blk((size_t)(4 * ctx->C.n_entry));
+    std::vector<uint32_t> dst((size_t)ctx->n_pair);
+    CK(cudaMemcpyAsync(dst.data(), ctx->C.pair_dst, sizeof(uint32_t) * dst.size(), cudaMemcpyDeviceToHost, s));
     std::vector<int32_t> e1(nt), e2(nt), nn((size_t)ctx->P.n_elem);
     std::vector<int64_t> po(nt);
     CK(cudaMemcpyAsync(blk.data(), ctx->blk_val, sizeof(double) * blk.size(), cudaMemcpyDeviceToHost, s));
@@ -431,19 +441,19 @@ int mofem_get_coo_values(mofem_ctx *ctx, double *V)
     int64_t off = 0;
     for (int64_t k = 0; k < nt; k++) {
         const int n1 = nn[e1[k]], n2 = nn[e2[k]];
-        const double *b = blk.data() + 4 * po[k];
+        const uint32_t *d = dst.data() + po[k];      // record of node pair (a, c) of this block
         for (int a = 0; a < n1; a++)
             for (int c = 0; c < n2; c++)
                 for (int p = 0; p < 2; p++)
                     for (int q = 0; q < 2; q++)
-                        out[off + (int64_t)(2 * a + p) * (2 * n2) + 2 * c + q] = b[4 * (a * n2 + c) + 2 * p + q];
+                        out[off + (int64_t)(2 * a + p) * (2 * n2) + 2 * c + q] = blk[4 * (size_t)d[a * n2 + c] + 2 * p + q];
         off += 4ll * n1 * n2;
         if (e1[k] != e2[k]) {
             for (int a = 0; a < n1; a++)
                 for (int c = 0; c < n2; c++)
                     for (int p = 0; p < 2; p++)
                         for (int q = 0; q < 2; q++)
-                            out[off + (int64_t)(2 * c + q) * (2 * n1) + 2 * a + p] = b[4 * (a * n2 + c) + 2 * p + q];
+                            out[off + (int64_t)(2 * c + q) * (2 * n1) + 2 * a + p] = blk[4 * (size_t)d[a * n2 + c] + 2 * p + q];
             off += 4ll * n1 * n2;
         }
     }
@@ -603,7 +613,10 @@ int mofem_spmv(mofem_ctx *ctx, const double *x, double *y)
     int rc;
     if (!is_device_ptr(x)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) return rc; CK(cudaMemcpyAsync(t, x, sizeof(double) * n, cudaMemcpyHostToDevice, s)); xd = t; }
     if (!is_device_ptr(y)) { double *t; if ((rc = dev_alloc(ctx, &t, n, tmp))) { free_pool(ctx, tmp); return rc; } yd = t; }
-    cudaError_t e = spmv(system_of(ctx), xd, yd, nullptr, s);
+    // row-partitioned mode: only the owned rows are computed; the ghost rows of y are returned as zeros
+    const DevSystem A = system_of(ctx);
+    cudaError_t e = A.n_own < n ? cudaMemsetAsync(yd + A.n_own, 0, sizeof(double) * (size_t)(n - A.n_own), s) : cudaSuccess;
+    if (e == cudaSuccess) e = spmv(A, xd, yd, nullptr, s);
     if (e == cudaSuccess && yd != y) e = cudaMemcpyAsync(y, yd, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     free_pool(ctx, tmp);

@@ -39,6 +39,13 @@ struct DevProblem {
 };
 
 // one task = one emitted block (regular element matrix, AMORE diagonal or off-diagonal block)
+// where the integration kernels store: blk_val in reduction order (csr.cu) through the inverse map of the sort
+struct BlkOut {
+    double *val;           // [4 Q] one 32-byte record per contribution
+    const uint32_t *dst;   // [off_t + n_pair] record of node pair s (task layout); [off_t + s]: record of its transposed copy
+    int64_t off_t;
+};
+
 struct DevTasks {
     int64_t n_task;
     int32_t *cell;      // [n_task]
@@ -72,7 +79,7 @@ cudaError_t launch_bucket_tasks(const DevTasks &t, int64_t *cls_count /*[N_CLASS
                                 int phase, cudaStream_t s);
 // integrates all tasks of one class; stats[0] += newton updates, stats[1] += evaluations, stats[2] = error flag
 cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *task_list,
-                                   int64_t n_list, double *blk_val, unsigned long long *stats, cudaStream_t s);
+                                   int64_t n_list, BlkOut blk_val, unsigned long long *stats, cudaStream_t s);
 
 // all-quad4 overlay cells with 1..3 incident elements and 1..5 straight triangles (class FAST_CLASS): one evaluation per
 // (point, element), blocks contracted out of shared memory, one launch.  Symbolic phase: one record per cell in sub-bucket order.
@@ -83,7 +90,7 @@ struct alignas(32) CqRec {
     int32_t slots;     // their mesh slots, 8 bits each
 };
 cudaError_t launch_cq_records(const DevProblem &p, const DevTasks &t, const int32_t *first_task, int64_t n, CqRec *rec, cudaStream_t s);
-cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count /*[N_SUB]*/, double *blk_val,
+cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count /*[N_SUB]*/, BlkOut blk_val,
                               unsigned long long *stats, cudaStream_t s);
 
 // csr.cu
@@ -96,7 +103,7 @@ struct DevCsr {
     int32_t *node_idx;    // [U] column node of each unique pair
     int32_t *pair_row;    // [U] row node of each unique pair
     int64_t *contrib_ptr; // [U+1] range of contributions of each unique pair
-    uint32_t *contrib_src;// [Q] (pair index in blk_val << 1) | transposed
+    uint32_t *pair_dst;   // [2 n_pair] record of blk_val (reduction order) that holds node pair s of the task layout; [n_pair + s]: its transposed copy (off-diagonal blocks only)
 };
 cudaError_t csr_count_rows(const DevProblem &p, const DevTasks &t, int32_t *row_cnt, cudaStream_t s);
 cudaError_t csr_fill_rows(const DevProblem &p, const DevTasks &t, const int64_t *row_start, int32_t *row_cursor,
@@ -105,6 +112,7 @@ cudaError_t csr_sort_rows(int64_t n_node, const int64_t *row_start, uint64_t *en
                           uint64_t *scratch, int *err_flag, int phase, cudaStream_t s);
 cudaError_t csr_emit(int64_t n_node, const int64_t *row_start, const uint64_t *entries, const int64_t *node_ptr,
                      int32_t *node_idx, int32_t *pair_row, int64_t *contrib_ptr, uint32_t *contrib_src, cudaStream_t s);
+cudaError_t csr_pair_dst(const DevCsr &c, const uint32_t *contrib_src /*[Q] sorted sources*/, int64_t n_pair, cudaStream_t s);
 cudaError_t csr_numeric(const DevCsr &c, const double *blk_val, double *data, cudaStream_t s);
 cudaError_t csr_export_pattern(const DevCsr &c, int32_t *indptr, int32_t *indices, cudaStream_t s);
 

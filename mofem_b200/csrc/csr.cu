@@ -6,13 +6,19 @@
 // a node pair (a,b) owns the scalar entries (2a+p, 2b+q).  The symbolic phase therefore works on node pairs
 // (4x fewer keys than COO triplets):
 //   1. count contributions per row node (integer atomics), prefix-sum -> row buckets
-//   2. fill buckets with keys (col_node << 32) | src,  src = (pair index in blk_val << 1) | transposed
+//   2. fill buckets with keys (col_node << 32) | src,  src = (node pair in task order << 1) | transposed
 //      -- src increases in emission order, so sorting the 64-bit key orders a row by (column, emission order)
 //      whatever order the atomics filled the bucket in
 //   3. one warp per row: bitonic sort of the bucket, count distinct columns
-//   4. prefix-sum -> node_ptr; emit node_idx / contrib_ptr / contrib_src
-// The numeric phase sums, for every unique node pair, its contributions in emission order (a fixed order:
-// bit-reproducible run to run) and writes the 2x2 sub-block into the scalar CSR rows 2a and 2a+1.
+//   4. prefix-sum -> node_ptr; emit node_idx / contrib_ptr / the sorted sources
+//   5. inverse map pair_dst: the record of blk_val every contribution is stored in
+// The integration kernels store every 2x2 block value straight into its record (blk_val is in REDUCTION order: the transposed
+// copy of an off-diagonal pair is a second 32-byte record), so the numeric phase is a pure, coalesced stream.  Record order:
+// the records of 32 consecutive unique node pairs (one warp of the numeric kernel) occupy the range their sorted runs occupy,
+// but ROUND-major: first the first contribution of every pair of the group, then the second of those that have one, ...
+// (a sliced-ELL layout without padding).  In round j the lanes that still have a contribution read consecutive records; every
+// pair still sums its contributions in emission order -- a fixed order: bit-reproducible run to run -- and writes the 2x2
+// sub-block into the scalar CSR rows 2a and 2a+1.
 // Scalar CSR layout: row 2a = [4*node_ptr[a], +2*deg), row 2a+1 = [4*node_ptr[a]+2*deg, 4*node_ptr[a+1]);
 // columns sorted, explicit zeros kept -- identical to scipy's canonical form.
 #include "common.cuh"
@@ -205,25 +211,59 @@ k_emit(int64_t n_node, const int64_t *__restrict__ row_start, const uint64_t *__
     }
 }
 
-// ---- numeric: segmented reduce in emission order ---------------------------------------------
+// ---- 5: record of every contribution (inverse map of the round-major order) -----------------------------------
+// thread per unique node pair, warp = group of 32 consecutive pairs; the numeric kernel walks the same rounds
 __global__ void __launch_bounds__(256)
-k_numeric(int64_t n_upair, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ pair_row,
-          const int64_t *__restrict__ contrib_ptr, const uint32_t *__restrict__ contrib_src,
-          const double *__restrict__ blk_val, double *__restrict__ data)
+k_pair_dst(int64_t n_upair, const int64_t *__restrict__ contrib_ptr, const uint32_t *__restrict__ contrib_src,
+           uint32_t *__restrict__ pair_dst, int64_t n_pair)
 {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_upair) return;
-    const int64_t cb = contrib_ptr[u], ce = contrib_ptr[u + 1];
-    double kxx = 0.0, kxy = 0.0, kyx = 0.0, kyy = 0.0;
-    for (int64_t c = cb; c < ce; c++) {
-        const uint32_t src = contrib_src[c];
-        // one 256-bit load per contribution (LDG.E.256 on sm_100): the 32-byte sector is looked up once, not twice
-        double a0, a1, a2, a3;
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
-                     : "l"(blk_val + 4 * (int64_t)(src >> 1)));
-        if (src & 1u) { kxx += a0; kxy += a2; kyx += a1; kyy += a3; }
-        else { kxx += a0; kxy += a1; kyx += a2; kyy += a3; }
+    const int lane = threadIdx.x & 31;
+    const bool valid = u < n_upair;
+    const int64_t cb = valid ? contrib_ptr[u] : 0;
+    const int len = valid ? (int)(contrib_ptr[u + 1] - cb) : 0;
+    int64_t base = __shfl_sync(0xffffffffu, cb, 0);
+    int maxlen = len;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
+    for (int j = 0; j < maxlen; j++) {
+        const unsigned m = __ballot_sync(0xffffffffu, len > j);
+        if (len > j) {
+            const uint32_t src = contrib_src[cb + j];
+            pair_dst[((src & 1u) ? n_pair : 0) + (int64_t)(src >> 1)] = (uint32_t)(base + __popc(m & ((1u << lane) - 1)));
+        }
+        base += __popc(m);
     }
+}
+
+// ---- numeric: segmented reduce in emission order ---------------------------------------------
+// thread per unique node pair, warp = group of 32 consecutive pairs whose records are stored round-major (see above): in round j
+// the lanes with more than j contributions read consecutive 32-byte records (one 256-bit load each)
+__global__ void __launch_bounds__(256)
+k_numeric(int64_t n_upair, const int64_t *__restrict__ node_ptr, const int32_t *__restrict__ pair_row,
+          const int64_t *__restrict__ contrib_ptr, const double *__restrict__ blk_val, double *__restrict__ data)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = u < n_upair;
+    const int64_t cb = valid ? contrib_ptr[u] : 0;
+    const int len = valid ? (int)(contrib_ptr[u + 1] - cb) : 0;
+    int64_t base = __shfl_sync(0xffffffffu, cb, 0);
+    int maxlen = len;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
+    double kxx = 0.0, kxy = 0.0, kyx = 0.0, kyy = 0.0;
+    for (int j = 0; j < maxlen; j++) {
+        const unsigned m = __ballot_sync(0xffffffffu, len > j);
+        if (len > j) {
+            double a0, a1, a2, a3;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
+                         : "l"(blk_val + 4 * (base + __popc(m & ((1u << lane) - 1)))));
+            kxx += a0; kxy += a1; kyx += a2; kyy += a3;
+        }
+        base += __popc(m);
+    }
+    if (!valid) return;
     const int64_t a = pair_row[u];
     const int64_t r0 = node_ptr[a], deg = node_ptr[a + 1] - r0;
     const int64_t kk = u - r0;
@@ -294,11 +334,18 @@ cudaError_t csr_emit(int64_t n_node, const int64_t *row_start, const uint64_t *e
     return cudaGetLastError();
 }
 
+cudaError_t csr_pair_dst(const DevCsr &c, const uint32_t *contrib_src, int64_t n_pair, cudaStream_t s)
+{
+    if (c.n_upair == 0) return cudaSuccess;
+    k_pair_dst<<<(unsigned)((c.n_upair + 255) / 256), 256, 0, s>>>(c.n_upair, c.contrib_ptr, contrib_src, c.pair_dst, n_pair);
+    return cudaGetLastError();
+}
+
 cudaError_t csr_numeric(const DevCsr &c, const double *blk_val, double *data, cudaStream_t s)
 {
     if (c.n_upair == 0) return cudaSuccess;
     k_numeric<<<(unsigned)((c.n_upair + 255) / 256), 256, 0, s>>>(c.n_upair, c.node_ptr, c.pair_row, c.contrib_ptr,
-                                                                   c.contrib_src, blk_val, data);
+                                                                   blk_val, data);
     return cudaGetLastError();
 }
 

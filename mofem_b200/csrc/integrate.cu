@@ -12,8 +12,9 @@
 //   S = sum w * [gx_a gx_b, gx_a gy_b, gy_a gx_b, gy_a gy_b];
 // 4 FMAs per (node pair, point) instead of the reference's dense 3-row products.
 //
-// Output layout (blk_val): per task, n1*n2 node pairs row-major, 4 doubles each
-//   [K(2a,2b), K(2a,2b+1), K(2a+1,2b), K(2a+1,2b+1)]   (one 32-byte sector per node pair).
+// Output (blk_val): one 32-byte record per CONTRIBUTION, [K(2a,2b), K(2a,2b+1), K(2a+1,2b), K(2a+1,2b+1)], stored straight at
+// its position in the reduction order of the CSR build (csr.cu: pair_dst); node pair s of the task layout (per task n1*n2 pairs,
+// row-major) goes to record pair_dst[s], the transposed copy of an off-diagonal pair to record pair_dst[off_t + s].
 //
 // Compiled with -fmad=false (see fem_device.cuh); accumulations use explicit fma().
 #include <cstdlib>
@@ -288,21 +289,33 @@ __device__ __forceinline__ void load_elem(const DevProblem &p, int e, double *X,
     }
 }
 
-// D applied to the four sums of one node pair -> the 2x2 sub-block, stored as one 32-byte sector
-__device__ __forceinline__ void store_pair(double *out, const double *D, double sxx, double sxy, double syx, double syy)
+__device__ __forceinline__ void store_record(double *rec, double a, double b, double c, double d)
+{   // one 256-bit store (STG.E.256): the record is written as a whole sector
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(rec), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// D applied to the four sums of node pair s (task layout) -> the 2x2 sub-block, stored as one 32-byte record at the pair's
+// position in the reduction order; off-diagonal blocks (both) also store the transposed sub-block
+__device__ __forceinline__ void apply_D(const double *D, double sxx, double sxy, double syx, double syy, double *k)
 {
-    double kxx = D[0] * sxx + D[2] * sxy + D[6] * syx + D[8] * syy;
-    double kxy = D[1] * sxy + D[2] * sxx + D[7] * syy + D[8] * syx;
-    double kyx = D[3] * syx + D[5] * syy + D[6] * sxx + D[8] * sxy;
-    double kyy = D[4] * syy + D[5] * syx + D[7] * sxy + D[8] * sxx;
-    reinterpret_cast<double2 *>(out)[0] = make_double2(kxx, kxy);
-    reinterpret_cast<double2 *>(out)[1] = make_double2(kyx, kyy);
+    k[0] = D[0] * sxx + D[2] * sxy + D[6] * syx + D[8] * syy;
+    k[1] = D[1] * sxy + D[2] * sxx + D[7] * syy + D[8] * syx;
+    k[2] = D[3] * syx + D[5] * syy + D[6] * sxx + D[8] * sxy;
+    k[3] = D[4] * syy + D[5] * syx + D[7] * sxy + D[8] * sxx;
+}
+__device__ __forceinline__ void store_pair(const BlkOut &o, int64_t s, bool both, const double *D, double sxx, double sxy, double syx,
+                                           double syy)
+{
+    double k[4];
+    apply_D(D, sxx, sxy, syx, syy, k);
+    store_record(o.val + 4 * (int64_t)o.dst[s], k[0], k[1], k[2], k[3]);
+    if (both) store_record(o.val + 4 * (int64_t)o.dst[o.off_t + s], k[0], k[2], k[1], k[3]);
 }
 
 // AMORE block (stiffnessMatrix.py:99-190): thread per task.
 template <int N1, int N2, bool CURVED>
 __global__ void __launch_bounds__(128)
-k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, double *__restrict__ blk_val,
+k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, BlkOut blk_val,
         unsigned long long *__restrict__ stats)
 {
     const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,9 +416,9 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
         const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[e1];  // off-diagonal blocks use element j's material (AMORE.py:113)
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
-        double *out = blk_val + 4 * t.pair_off[k];
+        const int64_t po = t.pair_off[k];
 #pragma unroll
-        for (int ab = 0; ab < N1 * N2; ab++) store_pair(out + 4 * ab, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
+        for (int ab = 0; ab < N1 * N2; ab++) store_pair(blk_val, po + ab, !diag, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
     }
     // statistics: warp-reduce then one atomic per warp (integers: order-independent)
 #pragma unroll
@@ -500,7 +513,7 @@ cudaError_t launch_cq_records(const DevProblem &p, const DevTasks &t, const int3
 template <int NE>
 __device__ __forceinline__ void
 cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cells, const int T, const int CB, const int cta,
-        double *__restrict__ blk_val, unsigned long long *__restrict__ stats)
+        BlkOut blk_val, unsigned long long *__restrict__ stats)
 {
     extern __shared__ double sm[];
     constexpr int TPC = NE * (NE + 1) / 2;                 // blocks (tasks) per cell
@@ -601,6 +614,17 @@ cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cel
         const double *r1 = cell + L.rows + ej * CQ_ROW + a;
         const double2 *r2 = reinterpret_cast<const double2 *>(cell + L.rows + el * CQ_ROW);
         const double *tg = cell + L.tri + 6;
+        // the blocks of a cell are consecutive in the task layout, 16 node pairs each; the records of this thread's four node pairs
+        // (and of their transposed copies) are fetched now and used after the accumulation
+        const int64_t s0 = *reinterpret_cast<const int64_t *>(cell + L.meta) + 16 * tk + 4 * a;
+        const bool both = ej != el;
+        uint32_t rec[4], rec_t[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int b = 0; b < 4; b++) rec[b] = __ldg(blk_val.dst + s0 + b);
+        if (both) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) rec_t[b] = __ldg(blk_val.dst + blk_val.off_t + s0 + b);
+        }
         double S[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) S[i] = 0.0;
@@ -628,10 +652,13 @@ cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cel
         double D[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
-        // the blocks of a cell are consecutive in blk_val, 16 node pairs each
-        double *out = blk_val + 4 * (*reinterpret_cast<const int64_t *>(cell + L.meta) + 16 * tk + 4 * a);
 #pragma unroll
-        for (int b = 0; b < 4; b++) store_pair(out + 4 * b, D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3]);
+        for (int b = 0; b < 4; b++) {
+            double k[4];
+            apply_D(D, S[4 * b], S[4 * b + 1], S[4 * b + 2], S[4 * b + 3], k);
+            store_record(blk_val.val + 4 * (int64_t)rec[b], k[0], k[1], k[2], k[3]);
+            if (both) store_record(blk_val.val + 4 * (int64_t)rec_t[b], k[0], k[2], k[1], k[3]);
+        }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -647,7 +674,7 @@ cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cel
 
 // All sub-buckets in ONE launch (the tails of the small sub-buckets overlap the big ones): a CTA looks its sub-bucket up in the plan.
 __global__ void __launch_bounds__(CQ_THREADS, CQ_MINB)
-k_cell_quads(DevProblem p, const CqRec *__restrict__ recs, CqPlan plan, double *__restrict__ blk_val,
+k_cell_quads(DevProblem p, const CqRec *__restrict__ recs, CqPlan plan, BlkOut blk_val,
              unsigned long long *__restrict__ stats)
 {
     int i = 0;
@@ -681,7 +708,7 @@ static int cq_batch(int ne, int T)
 
 // sub_count: cells in the N_SUB sub-buckets of class FAST_CLASS; sub-bucket (ne - 1) * 5 + T - 1 = the cells with ne incident quads
 // and T triangles, whose records follow each other in `recs` in sub-bucket order (the last sub-bucket holds no cells)
-cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count, double *blk_val,
+cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int64_t *sub_count, BlkOut blk_val,
                               unsigned long long *stats, cudaStream_t s)
 {
     CqPlan plan{};
@@ -716,7 +743,7 @@ cudaError_t launch_cell_quads(const DevProblem &p, const CqRec *recs, const int6
 // Regular elements: triFE (1 pt) / triQuadFE (3 pts) / quadFE (2x2) / quadQuadFE (3x3), stiffnessMatrix.py:9-81.
 template <int N>
 __global__ void __launch_bounds__(128)
-k_regular(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, double *__restrict__ blk_val)
+k_regular(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, BlkOut blk_val)
 {
     const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_list) return;
@@ -759,14 +786,14 @@ k_regular(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64
     const double *Dp = p.mat_D + 9 * (int64_t)p.elem_mat[e];
 #pragma unroll
     for (int i = 0; i < 9; i++) D[i] = Dp[i];
-    double *out = blk_val + 4 * t.pair_off[k];
+    const int64_t po = t.pair_off[k];
 #pragma unroll
-    for (int ab = 0; ab < N * N; ab++) store_pair(out + 4 * ab, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
+    for (int ab = 0; ab < N * N; ab++) store_pair(blk_val, po + ab, false, D, S[4 * ab], S[4 * ab + 1], S[4 * ab + 2], S[4 * ab + 3]);
 }
 
 // ICMFE (stiffnessMatrix.py:49-67, shapeFunction.py:53-73): quad4 + two incompatible modes, static condensation.
 __global__ void __launch_bounds__(128)
-k_icm(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, double *__restrict__ blk_val)
+k_icm(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n_list, BlkOut blk_val)
 {
     const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_list) return;
@@ -840,19 +867,23 @@ k_icm(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t n
             Xs[8 * r + j] = sacc / H[4 * r + r];
         }
     }
-    double *out = blk_val + 4 * t.pair_off[k];
-    for (int i = 0; i < 8; i++)
-        for (int j = 0; j < 8; j++) {
-            double acc = A[12 * i + 8] * Xs[j];
-            for (int c = 1; c < 4; c++) acc = fma(A[12 * i + 8 + c], Xs[8 * c + j], acc);
-            const double v = A[12 * i + j] - acc;
-            out[4 * ((i >> 1) * 4 + (j >> 1)) + 2 * (i & 1) + (j & 1)] = v;
+    const int64_t po = t.pair_off[k];
+    for (int i = 0; i < 8; i += 2)
+        for (int j = 0; j < 8; j += 2) {
+            double v[4];
+            for (int pq = 0; pq < 4; pq++) {
+                const int ii = i + (pq >> 1), jj = j + (pq & 1);
+                double acc = A[12 * ii + 8] * Xs[jj];
+                for (int c = 1; c < 4; c++) acc = fma(A[12 * ii + 8 + c], Xs[8 * c + jj], acc);
+                v[pq] = A[12 * ii + jj] - acc;
+            }
+            store_record(blk_val.val + 4 * (int64_t)blk_val.dst[po + (i >> 1) * 4 + (j >> 1)], v[0], v[1], v[2], v[3]);
         }
 }
 
 template <int N1, int N2>
 static cudaError_t launch_amore(bool curved, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
-                                double *blk_val, unsigned long long *stats, cudaStream_t s)
+                                BlkOut blk_val, unsigned long long *stats, cudaStream_t s)
 {
     const unsigned grid = (unsigned)((n + 127) / 128);
     if (curved) k_amore<N1, N2, true><<<grid, 128, 0, s>>>(p, t, list, n, blk_val, stats);
@@ -862,7 +893,7 @@ static cudaError_t launch_amore(bool curved, const DevProblem &p, const DevTasks
 
 template <int N1>
 static cudaError_t launch_amore_n2(int i2, bool curved, const DevProblem &p, const DevTasks &t, const int32_t *list,
-                                   int64_t n, double *blk_val, unsigned long long *stats, cudaStream_t s)
+                                   int64_t n, BlkOut blk_val, unsigned long long *stats, cudaStream_t s)
 {
     switch (i2) {
     case 0: return launch_amore<N1, 3>(curved, p, t, list, n, blk_val, stats, s);
@@ -873,7 +904,7 @@ static cudaError_t launch_amore_n2(int i2, bool curved, const DevProblem &p, con
 }
 
 cudaError_t launch_integrate_class(int cls, const DevProblem &p, const DevTasks &t, const int32_t *list, int64_t n,
-                                   double *blk_val, unsigned long long *stats, cudaStream_t s)
+                                   BlkOut blk_val, unsigned long long *stats, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);

@@ -13,6 +13,11 @@ from . import _lib
 from .flatten import FlatProblem
 
 
+_PROBLEM_DTYPES = dict(node_xy=np.float64, elem_nodes=np.int32, elem_nn=np.int32, elem_mat=np.int32, mat_D=np.float64,
+                       cell_elem=np.int32, cell_kind=np.int32, cell_tri_ptr=np.int64, tri_xy=np.float64, tri_rho=np.float64,
+                       tri_mid=np.float64, tri_curved=np.uint8)
+
+
 def _c(a, dtype):
     return None if a is None else np.ascontiguousarray(a, dtype=dtype)
 
@@ -50,6 +55,10 @@ class Context:
     def __exit__(self, *a):
         self.close()
 
+    def _p(self, a, dtype):
+        """Validated raw pointer: exact dtype, contiguous, and (CUDA tensors) on this context's GPU."""
+        return _lib.ptr(a, dtype, self.device)
+
     def _ck(self, rc):
         _lib.raise_for(rc, self._h)
 
@@ -60,7 +69,7 @@ class Context:
 
     # -- assembly --------------------------------------------------------------------------
     @staticmethod
-    def problem_struct(fp: FlatProblem):
+    def problem_struct(fp: FlatProblem, device=None):
         """(struct, keep-alive dict) for a flattened problem held in host numpy arrays or torch tensors."""
         def arr(a, dt):
             if a is None or hasattr(a, "data_ptr"):
@@ -75,11 +84,11 @@ class Context:
         s = _lib.MofemProblem(
             n_node=int(k["node_xy"].shape[0]), n_elem=int(k["elem_nn"].shape[0]), n_cell=int(k["cell_kind"].shape[0]),
             n_tri=int(k["tri_xy"].shape[0]), n_mesh=int(fp.n_mesh), n_mat=int(k["mat_D"].shape[0]),
-            solver=int(fp.solver), **{name: _lib.ptr(v) for name, v in k.items()})
+            solver=int(fp.solver), **{name: _lib.ptr(v, _PROBLEM_DTYPES[name], device, name) for name, v in k.items()})
         return s, k
 
     def set_problem(self, fp: FlatProblem):
-        s, keep = self.problem_struct(fp)
+        s, keep = self.problem_struct(fp, self.device)
         self._ck(self._L.mofem_set_problem(self._h, C.byref(s)))
         self._keep = keep
         self.n_dof = 2 * int(s.n_node)
@@ -104,7 +113,7 @@ class Context:
         indptr = np.empty(i["n_dof"] + 1, np.int32)
         indices = np.empty(i["nnz"], np.int32)
         data = np.empty(i["nnz"], np.float64) if values else None
-        self._ck(self._L.mofem_get_csr(self._h, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data)))
+        self._ck(self._L.mofem_get_csr(self._h, self._p(indptr, np.int32), self._p(indices, np.int32), self._p(data, np.float64)))
         return indptr, indices, data
 
     def csr_matrix(self):
@@ -116,7 +125,7 @@ class Context:
     def coo_values(self):
         """``Vglo`` in the reference's emission order (parity / debug)."""
         V = np.empty(self.info()["n_coo"], np.float64)
-        self._ck(self._L.mofem_get_coo_values(self._h, _lib.ptr(V)))
+        self._ck(self._L.mofem_get_coo_values(self._h, self._p(V, np.float64)))
         return V
 
     # -- solve -----------------------------------------------------------------------------
@@ -127,14 +136,14 @@ class Context:
         for a in (rhs, fixed, fixed_value):
             if a.shape[0] != self.n_dof:
                 raise ValueError(f"system arrays must have {self.n_dof} entries")
-        self._ck(self._L.mofem_set_system(self._h, _lib.ptr(rhs), _lib.ptr(fixed), _lib.ptr(fixed_value)))
+        self._ck(self._L.mofem_set_system(self._h, self._p(rhs, np.float64), self._p(fixed, np.uint8), self._p(fixed_value, np.float64)))
         return self
 
     def solve(self, rtol=1e-12, maxit=200000, out=None, check=True):
         """Jacobi-PCG; returns (u, info dict).  ``out`` may be a numpy array or a CUDA tensor."""
         u = np.empty(self.n_dof, np.float64) if out is None else out
         si = _lib.MofemSolveInfo()
-        rc = self._L.mofem_solve(self._h, float(rtol), int(maxit), _lib.ptr(u), C.byref(si))
+        rc = self._L.mofem_solve(self._h, float(rtol), int(maxit), self._p(u, np.float64), C.byref(si))
         info = dict(iterations=si.iterations, converged=int(si.converged), relres_true=si.relres_true,
                     relres_rec=si.relres_rec, restarts=si.restarts)
         if rc == _lib.E_NOCONV and not check:
@@ -150,20 +159,21 @@ class Context:
     def spmv(self, x, out=None):
         x = x if hasattr(x, "data_ptr") else _c(np.asarray(x).reshape(-1), np.float64)
         y = np.empty(self.n_dof, np.float64) if out is None else out
-        self._ck(self._L.mofem_spmv(self._h, _lib.ptr(x), _lib.ptr(y)))
+        self._ck(self._L.mofem_spmv(self._h, self._p(x, np.float64), self._p(y, np.float64)))
         return y
 
     def assemble_solve(self, fp: FlatProblem, rhs, fixed, fixed_value, rtol=1e-12, maxit=200000):
         """One call, host buffers in / host displacement out (the end-to-end timing path)."""
-        s, keep = self.problem_struct(fp)
+        s, keep = self.problem_struct(fp, self.device)
         rhs = _c(np.asarray(rhs).reshape(-1), np.float64)
         fixed = _c(np.asarray(fixed).reshape(-1), np.uint8)
         fixed_value = _c(np.asarray(fixed_value).reshape(-1), np.float64)
         u = np.empty(2 * int(s.n_node), np.float64)
         e = C.c_double(0.0)
         si = _lib.MofemSolveInfo()
-        rc = self._L.mofem_assemble_solve(self._h, C.byref(s), _lib.ptr(rhs), _lib.ptr(fixed), _lib.ptr(fixed_value),
-                                          float(rtol), int(maxit), _lib.ptr(u), C.byref(e), C.byref(si))
+        rc = self._L.mofem_assemble_solve(self._h, C.byref(s), self._p(rhs, np.float64), self._p(fixed, np.uint8),
+                                          self._p(fixed_value, np.float64), float(rtol), int(maxit), self._p(u, np.float64),
+                                          C.byref(e), C.byref(si))
         self._keep = keep
         self.n_dof = 2 * int(s.n_node)
         self._ck(rc)
@@ -235,8 +245,9 @@ class Context:
             out = np.empty((V, M))
         nw = C.c_int64(0)
         ms = C.c_double(0)
-        self._ck(self._L.mofem_rho_eval(self._h, V, M, _lib.ptr(vert_xy), _lib.ptr(vert_elem), int(elem_nv.shape[0]),
-                                        _lib.ptr(elem_nv), _lib.ptr(elem_xy), _lib.ptr(elem_w), _lib.ptr(out),
+        self._ck(self._L.mofem_rho_eval(self._h, V, M, self._p(vert_xy, np.float64), self._p(vert_elem, np.int32), int(elem_nv.shape[0]),
+                                        self._p(elem_nv, np.int32), self._p(elem_xy, np.float64), self._p(elem_w, np.float64),
+                                        self._p(out, np.float64),
                                         C.byref(nw), C.byref(ms)))
         return out, int(nw.value), float(ms.value)
 

@@ -60,3 +60,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "mofem_oracle" not in src, f
+
+
+def test_pointer_validation_rejects_reinterpretable_arrays():
+    """The C-ABI takes raw pointers: the binding refuses arrays it would otherwise reinterpret (wrong element type, strided view)."""
+    import numpy as np
+    import torch
+    from mofem_b200 import _lib
+    ok = np.zeros(6)
+    assert _lib.ptr(ok, np.float64) == ok.ctypes.data and _lib.ptr(None, np.float64) is None
+    with pytest.raises(TypeError):
+        _lib.ptr(np.zeros(6, np.float32), np.float64, what="rhs")
+    with pytest.raises(TypeError):
+        _lib.ptr(np.zeros(6, np.int64), np.int32)
+    with pytest.raises(ValueError):
+        _lib.ptr(np.zeros((6, 2))[:, 0], np.float64)
+    t = torch.zeros(6, dtype=torch.float64)
+    assert _lib.ptr(t, np.float64) == t.data_ptr()
+    with pytest.raises(TypeError):
+        _lib.ptr(torch.zeros(6, dtype=torch.float32), np.float64)
+    with pytest.raises(ValueError):
+        _lib.ptr(torch.zeros(6, 2, dtype=torch.float64)[:, 0], np.float64)
