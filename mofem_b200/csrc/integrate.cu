@@ -296,12 +296,14 @@ __device__ __forceinline__ void store_record(double *rec, double a, double b, do
 
 // D applied to the four sums of node pair s (task layout) -> the 2x2 sub-block, stored as one 32-byte record at the pair's
 // position in the reduction order; off-diagonal blocks (both) also store the transposed sub-block
+// D applied to the four sums of a node pair.  Not an ill-conditioned step (see fem_device.cuh): contracted into fused chains,
+// 4 instructions per entry instead of 7.
 __device__ __forceinline__ void apply_D(const double *D, double sxx, double sxy, double syx, double syy, double *k)
 {
-    k[0] = D[0] * sxx + D[2] * sxy + D[6] * syx + D[8] * syy;
-    k[1] = D[1] * sxy + D[2] * sxx + D[7] * syy + D[8] * syx;
-    k[2] = D[3] * syx + D[5] * syy + D[6] * sxx + D[8] * sxy;
-    k[3] = D[4] * syy + D[5] * syx + D[7] * sxy + D[8] * sxx;
+    k[0] = fma(D[8], syy, fma(D[6], syx, fma(D[2], sxy, D[0] * sxx)));
+    k[1] = fma(D[8], syx, fma(D[7], syy, fma(D[2], sxx, D[1] * sxy)));
+    k[2] = fma(D[8], sxy, fma(D[6], sxx, fma(D[5], syy, D[3] * syx)));
+    k[3] = fma(D[8], sxx, fma(D[7], sxy, fma(D[5], syx, D[4] * syy)));
 }
 __device__ __forceinline__ void store_pair(const BlkOut &o, int64_t s, bool both, const double *D, double sxx, double sxy, double syx,
                                            double syy)
