@@ -654,6 +654,10 @@ cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cel
         double D[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) D[i] = Dp[i];
+        // keep the fetched record numbers opaque until here: otherwise their address arithmetic is scheduled right behind the loads
+        // and the warp waits for them BEFORE the accumulation instead of during it
+#pragma unroll
+        for (int b = 0; b < 4; b++) { asm volatile("" : "+r"(rec[b])); asm volatile("" : "+r"(rec_t[b])); }
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             double k[4];
