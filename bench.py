@@ -119,19 +119,24 @@ def algorithmic_bytes(info, n_dof):
         # SURVEY.md section 8d scalar-CSR figure for the same product (12 B per stored entry)
         "spmv_scalar_csr": 12 * nnz + 4 * (n_dof + 1) + 16 * n_dof,
         "vec": 8 * n_dof * 8,            # k_pcg_vec: reads q, r, dinv, p, x; writes r, x, p (p's second read comes out of L2)
-        # numeric reduce: every block value once (32 B per node pair), its 4 B source slot, CSR values out
-        "numeric": 32 * n_pair + 4 * n_contrib + 8 * nnz,
+        # numeric reduce (block values stored in reduction order): every contribution record once (32 B; the transposed copy of an
+        # off-diagonal pair is its own record), per unique node pair its run pointer (8 B) and row node (4 B), CSR values out
+        "numeric": 32 * n_contrib + 12 * (nnz // 4) + 8 * nnz,
+        # the same reduce with round 1's layout (32 B per stored node pair + a 4 B source slot per contribution): kept for comparison
+        "numeric_r1_layout": 32 * n_pair + 4 * n_contrib + 8 * nnz,
     }
 
 
 FP64_PEAK_TFLOPS = 37.2     # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (ncu: 9472 DFMA thread-inst/clk peak)
 
 
-def integration_flops(fp, info, ms):
+def integration_flops(fp, info, ms, cell_kernel=True):
     """fp64 roofline of the integration kernels with SURVEY.md section 8d's flop model for quad4 overlays: per evaluation
     87 k + 167 (k Newton updates), per (point, block) contraction 304, regular quad4 element 4 x (95 + 304).
-    ``algorithmic`` counts ONE evaluation per (point, incident element) -- the minimum; ``executed`` counts what the
-    thread-per-block kernels (like the reference) do: the off-diagonal block re-evaluates both elements."""
+    ``algorithmic`` counts ONE evaluation per (point, incident element) -- the minimum, and what the cell kernel (k_cell_quads, the
+    default for all-quad4 overlay cells with <= 3 elements and <= 5 straight triangles) executes; ``reference_order`` counts what
+    the thread-per-block kernels (like the reference) do: every block re-evaluates its elements.  ``executed`` = the count of the
+    kernels that ran (``cell_kernel`` = the library option)."""
     if not (np.asarray(fp.elem_nn) == 4).all():
         # the survey's flop model is written for quad4 elements; tri3 patches (closed-form inverse map, 3/4-point rules) only get counts
         return {"newton_updates_per_evaluation": info["newton_updates"] / max(info["n_eval"], 1), "fp64_peak_tflops": FP64_PEAK_TFLOPS,
@@ -149,12 +154,18 @@ def integration_flops(fp, info, ms):
     f_eval = 87.0 * kbar + 167.0
     regular = float((~overlay).sum()) * 4 * (95 + 304)
     alg = evals_min * f_eval + contractions * 304 + regular
+    ref_order = evals_done * f_eval + contractions * 304 + regular
+    if cell_kernel:     # cells outside the cell kernel's range (more than 3 elements / 5 triangles, curved) stay on the block kernels
+        fast = (mo <= 3) & (tri[overlay] <= 5) & (tri[overlay] >= 1)
+        if getattr(fp, "tri_curved", None) is not None and np.asarray(fp.tri_curved).any():
+            fast &= False
+        evals_done = float((points * mo * np.where(fast, 1, mo)).sum())
     done = evals_done * f_eval + contractions * 304 + regular
     return {"newton_updates_per_evaluation": kbar, "algorithmic_gflop": alg / 1e9, "executed_gflop": done / 1e9,
             "algorithmic_tflops": alg / (ms * 1e-3) / 1e12, "executed_tflops": done / (ms * 1e-3) / 1e12,
             "fp64_peak_tflops": FP64_PEAK_TFLOPS, "frac_fp64_algorithmic": alg / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
             "frac_fp64_executed": done / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-            "evaluations_model": evals_done}
+            "evaluations_model": evals_done, "reference_order_gflop": ref_order / 1e9, "cell_kernel": bool(cell_kernel)}
 
 
 RUNNER = os.path.join(REPO, "baseline", "ref_runner.py")
@@ -787,7 +798,7 @@ def main():
     spmv_ms = prof["spmv_ms"] / iters if prof["iterations"] else None
     roofline = None
     traffic = None    # dram__bytes_read + dram__bytes_write per SpMV launch, from the committed ncu capture of this workload
-    tpath = os.path.join(REPO, "profiles", "r1_spmv_traffic.json")
+    tpath = os.path.join(REPO, "profiles", "r2_spmv_traffic.json")
     if world == 1 and args.n0 == 664 and args.family == "quad" and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["dram_bytes_per_launch"]
@@ -812,7 +823,9 @@ def main():
                                 "frac_hbm": ab["vec"] / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     nm = phases["numeric_ms"] / args.steps
     kernels["k_numeric"] = {"avg_launch_ms": nm, "gbs": ab["numeric"] / (nm * 1e-3) / 1e9,
-                            "frac_hbm": ab["numeric"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                            "frac_hbm": ab["numeric"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                            "algorithmic_bytes": ab["numeric"],
+                            "frac_hbm_r1_layout_bytes": ab["numeric_r1_layout"] / (nm * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     im = phases["integrate_ms"] / args.steps
     kernels["integrate (all classes)"] = {"ms": im, "cells_per_s": fp.n_cell / (im * 1e-3),
                                           "newton_updates": info["newton_updates"], "evaluations": info["n_eval"]}
