@@ -520,6 +520,22 @@ def rank_problem(n0, family, strong, rank, world, host_overlay=False):
     return part, part.local_vector(rhs_g), part.local_vector(fixed_g), part.local_vector(val_g), own_cells
 
 
+def scaling_decomposition(args, world, iterations, it_per_s):
+    """N > 1, default weak-scaling workload: the two causes of value(N) / (N value(1)) < 1 kept apart.  The 1-GPU side comes
+    from the committed 1-GPU line of the same block (profiles/r2_bench_1gpu.json), it is NOT measured in this run."""
+    ref = os.path.join(REPO, "profiles", "r2_bench_1gpu.json")
+    if world == 1 or args.strong or args.family != "quad" or args.n0 != 664 or not os.path.exists(ref):
+        return None
+    with open(ref) as f:
+        one = json.loads(f.read().strip().splitlines()[-1])["pcg"]
+    return {"pcg_iterations": iterations, "pcg_iterations_1gpu": one["iterations"],
+            "iteration_growth": iterations / one["iterations"],
+            "iterations_per_s": it_per_s, "iterations_per_s_1gpu": one["iterations_per_s"],
+            "per_iteration_efficiency": it_per_s / one["iterations_per_s"],
+            "note": "weak scaling stacks N blocks of n0 x n0: Jacobi-PCG needs more iterations on the taller domain (algorithmic); the "
+                    "per-iteration rate is what the transport costs.  1-GPU figures: profiles/r2_bench_1gpu.json (committed, not measured here)"}
+
+
 def stack_loads(rhs_g, n0, blocks):
     for r in range(1, blocks):
         nd = r * n0 * (n0 + 1) + n0
@@ -863,6 +879,7 @@ def main():
         "pcg": {"iterations": si["iterations"], "converged": si["converged"], "relres_true": si["relres_true"],
                 "restarts": si["restarts"], "iterations_per_s": si["iterations"] / (phases["solve_ms"] / args.steps * 1e-3)},
         "kernels": kernels,
+        "scaling_decomposition": scaling_decomposition(args, world, si["iterations"], si["iterations"] / (phases["solve_ms"] / args.steps * 1e-3)),
         "energy": last["energy"],
         "parity_check": parity,
         "prep_s": prep_s,
