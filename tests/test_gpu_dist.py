@@ -45,6 +45,7 @@ def _worker(rank, world, port, out, transport, ny=NY):
             # ghost entries of the returned local vector are current
             assert np.array_equal(u_loc, part.local_vector(u))
         out[rank] = (u, info, energy)
+        out[("n_owned", rank)] = int(part.n_owned_node)
     finally:
         dist.destroy_process_group()
 
@@ -67,6 +68,10 @@ def test_two_gpu_solve_matches_single_gpu(gpu_ctx, transport):
         out = mgr.dict()
         mp.spawn(_worker, args=(WORLD, port, out, transport), nprocs=WORLD, join=True)
         res = [out[r] for r in range(WORLD)]
+        owned = [out[("n_owned", r)] for r in range(WORLD)]
+    # a rank with an ODD owned-node count: its last owned node and its first ghost node share one 32-byte sector of p, the case in
+    # which a stale non-coherent read of the ghost would show (the halo rows read ghosts with ld.global.cg)
+    assert any(n % 2 for n in owned), owned
     for u, info, energy in res:
         assert info["converged"] == 1
         assert np.abs(u - u1).max() <= 1e-9 * np.abs(u1).max()
