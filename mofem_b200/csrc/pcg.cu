@@ -611,9 +611,21 @@ k_pcg_direction(int64_t n2, int it, double *__restrict__ sc, const double2 *__re
 // The iteration that meets the tolerance still updates x; p is left and the stop flag goes up.
 constexpr int FUSE_BLOCK = 256, FUSE_EPT = 6, FUSE_BPS = 3;
 
+// first batch of the residual update: D^-1 and r of the thread's first FUSE_EPT elements.  Neither is written by the SpMV, so the
+// loads are issued BEFORE the grid dependency / the mailbox wait and overlap the tail of the SpMV.
+__device__ __forceinline__ void vec_preload(int64_t n2, int64_t tid, int64_t nth, const double2 *__restrict__ dinv,
+                                            const double2 *__restrict__ r, double2 (&dpre)[FUSE_EPT], double2 (&rpre)[FUSE_EPT])
+{
+#pragma unroll
+    for (int e = 0; e < FUSE_EPT; e++) {
+        const int64_t i = tid + e * nth;
+        if (i < n2) { dpre[e] = dinv[i]; rpre[e] = r[i]; }
+    }
+}
+
 __device__ __forceinline__ void vec_phase1(int64_t n2, int64_t tid, int64_t nth, double alpha, const double2 *__restrict__ q,
                                            const double2 *__restrict__ dinv, double2 *__restrict__ r, double2 (&zc)[FUSE_EPT],
-                                           double &rz, double &rr)
+                                           const double2 (&dpre)[FUSE_EPT], const double2 (&rpre)[FUSE_EPT], double &rz, double &rr)
 {
     auto residual = [&](int64_t i, double2 qi, double2 di, double2 ri) {
         ri.x = fma(-alpha, qi.x, ri.x); ri.y = fma(-alpha, qi.y, ri.y);
@@ -626,7 +638,7 @@ __device__ __forceinline__ void vec_phase1(int64_t n2, int64_t tid, int64_t nth,
 #pragma unroll
     for (int e = 0; e < FUSE_EPT; e++) {       // first batch: z stays in registers (the compiler interleaves the loads)
         const int64_t i = tid + e * nth;
-        if (i < n2) zc[e] = residual(i, q[i], dinv[i], r[i]);
+        if (i < n2) zc[e] = residual(i, q[i], dpre[e], rpre[e]);
     }
     constexpr int B1 = 2;                      // later batches (large problems, DRAM-bound): loads of a batch issued together
     for (int64_t base = tid + FUSE_EPT * nth; base < n2; base += B1 * nth) {
@@ -709,6 +721,9 @@ k_pcg_vec(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, 
 {
     __shared__ double sm[FUSE_BLOCK / 32];
     __shared__ bool is_last;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    double2 dpre[FUSE_EPT], rpre[FUSE_EPT];
+    vec_preload(n2, tid, nth, dinv, r, dpre, rpre);     // r and D^-1 are not the SpMV's to write: fetched ahead of the dependency
     ring::grid_dep_wait();        // PDL: no-op unless launched with the programmatic-serialization attribute
     if (__ldcg(sc + SC_DONE) != 0.0 || *reinterpret_cast<volatile int *>(err)) return;   // stopped, or an earlier wait timed out
     double pq, unused;
@@ -720,10 +735,9 @@ k_pcg_vec(int64_t n2, int it, double *__restrict__ sc, double2 *__restrict__ p, 
     } else pq = __ldcg(sc + SC_PQ);
     const double rz_old = __ldcg(sc + sc_rz(it));
     const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     double2 zc[FUSE_EPT];
     double rz = 0.0, rr = 0.0;
-    vec_phase1(n2, tid, nth, alpha, q, dinv, r, zc, rz, rr);
+    vec_phase1(n2, tid, nth, alpha, q, dinv, r, zc, dpre, rpre, rz, rr);
     const double s1 = block_sum(rz, sm);
     const double s2 = block_sum(rr, sm);
     // arrive
