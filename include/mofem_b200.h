@@ -204,9 +204,10 @@ int mofem_set_profile(mofem_ctx *ctx, int on);
  * (0: row kernel); "pdl" [1] programmatic dependent launch between the two kernels of a PCG iteration (single GPU and peer
  * transport, with the ring); "floor_rtol_1e12" [10000] = 1e12 x the largest TRUE relative residual mofem_solve still accepts
  * (converged = 2) when restarts no longer reduce it -- above max(rtol, that) the solve returns MOFEM_E_NOCONV; "l2_persist" [0] / "l2_window" [5] L2 persistence window over the first
- * N PCG vectors during mofem_solve (measured neutral at 1 M cells, harmful at 10 M); "cell_kernel" [0] sends quad4 overlay
- * cells to the warp-cooperative cell kernel instead of the thread-per-block kernels (bit-identical results, measured slower on
- * B200 -- see DESIGN.md; set before mofem_symbolic). */
+ * N PCG vectors during mofem_solve (measured neutral at 1 M cells, harmful at 10 M); "cell_kernel" [1] integrates overlay
+ * cells whose incident elements are all 4-node quads (<= 3 of them, <= 5 straight triangles) per CELL -- one evaluation per
+ * (point, element) -- instead of per block (0: thread-per-block kernels for everything; bit-identical results, 2.2x slower on
+ * the synthetic families -- see DESIGN.md; set before mofem_symbolic). */
 int mofem_set_option(mofem_ctx *ctx, const char *name, int64_t value);
 int mofem_get_pcg_profile(mofem_ctx *ctx, double ms[3], int64_t *iterations);
 

@@ -111,18 +111,19 @@ def test_spmv_matches_scipy(gpu_ctx):
     assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
 
 
-@pytest.mark.parametrize("name", ["patch16", "patch16_m3", "simpleOFE3", "zoo_s1"])
+@pytest.mark.parametrize("name", ["patch16", "patch16_m3", "patch16_m3s", "patch32_m3s", "patch16_tri", "simpleOFE3", "zoo_s1"])
 def test_cell_kernel_is_bit_identical_to_the_block_kernels(gpu_ctx, name):
-    """The warp-cooperative quad4 cell kernel (one evaluation per point and element, shared-memory transpose) keeps the
-    per-block kernels' fma order: identical bits, identical Newton counts."""
+    """The cell kernel (all-quad4 overlay cells with 1..3 incident elements: one evaluation per point and element, strain pairs
+    through shared memory, the library default) keeps the per-block kernels' fma order: identical bits -- block values and
+    assembled CSR values -- and identical Newton counts.  patch*_m3s have cells with three incident elements; patch16_tri and
+    the shipped decks have cells the cell kernel must leave to the block kernels."""
     fp, d = load_golden(name)
-    gpu_ctx.set_option("cell_kernel", 0)
-    gpu_ctx.set_problem(fp).symbolic().assemble()
-    a, na = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"]
-    gpu_ctx.set_option("cell_kernel", 1)
     try:
-        gpu_ctx.set_problem(fp).symbolic().assemble()
-        b, nb = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"]
-    finally:
         gpu_ctx.set_option("cell_kernel", 0)
-    assert np.array_equal(a, b) and na == nb
+        gpu_ctx.set_problem(fp).symbolic().assemble()
+        a, na, da = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"], gpu_ctx.csr()[2]
+    finally:
+        gpu_ctx.set_option("cell_kernel", 1)       # the default: the session context goes on with it
+    gpu_ctx.set_problem(fp).symbolic().assemble()
+    b, nb, db = gpu_ctx.coo_values(), gpu_ctx.info()["newton_updates"], gpu_ctx.csr()[2]
+    assert np.array_equal(a, b) and np.array_equal(da, db) and na == nb
