@@ -292,8 +292,7 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(cudaMemsetAsync(row_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_node, 1), s));
     CKT(csr_count_rows(P, T, row_cnt, s)); L++;
     CKT(exclusive_scan_i32_to_i64(row_cnt, C.row_start, P.n_node, C.row_start + P.n_node, s, &L));
-    CKT(cudaMemcpyAsync(&C.n_entry, C.row_start + P.n_node, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CKT(cudaStreamSynchronize(s));
+    C.n_entry = ctx->n_coo / 4;        // every contribution (a node pair of a block, or its transposed copy) is four COO triplets: no read-back
     if (C.n_entry >= (1ll << 32)) {
         cleanup();
         return ctx_fail(ctx, MOFEM_E_LIMIT, "more than 2^32 block contributions on one device: shard the cells over more GPUs");
