@@ -774,9 +774,11 @@ def main():
 
     # ---- end to end through the public API with pinned host buffers -----------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_warm = 1 if args.warmup > 0 else 0       # one untimed pass of this path (its staging buffers come out of the pool afterwards)
+    for k_e2e in range(e2e_warm + e2e_steps):
+        if k_e2e == e2e_warm:
+            barrier()
+            t0 = time.perf_counter()
         if part is None:
             u_h, energy_h, si_h = ctx.assemble_solve(fp_host, host_sys["rhs"].numpy(), host_sys["fixed"].numpy(),
                                                      host_sys["val"].numpy(), rtol=args.rtol, maxit=maxit)
