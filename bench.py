@@ -848,6 +848,12 @@ def main():
     kernels["integrate (all classes)"] = {"ms": im, "cells_per_s": fp.n_cell / (im * 1e-3),
                                           "newton_updates": info["newton_updates"], "evaluations": info["n_eval"]}
     kernels["integrate (all classes)"].update(integration_flops(fp, info, im))
+    if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and "frac_fp64_algorithmic" in kernels["integrate (all classes)"]:
+        # the assembly of a step starts right behind ~0.6 s of PCG at the power cap, so it runs at the capped SM clock: the same
+        # fraction against the fp64 peak AT THAT CLOCK (median SM clock sampled during the timed region) next to the nominal one
+        k = kernels["integrate (all classes)"]
+        k["sm_mhz_during_run"] = clocks["sm_mhz"]
+        k["frac_fp64_algorithmic_at_run_clock"] = k["frac_fp64_algorithmic"] * 1965.0 / clocks["sm_mhz"]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
