@@ -583,8 +583,10 @@ cq_body(const DevProblem &p, const CqRec *__restrict__ recs, const int64_t n_cel
     }
     __syncthreads();
     // ---- phase 1: one evaluation per (cell, point, element)
-    for (int ev = tid; ev < nb * EPC; ev += CQ_THREADS) {
-        const int ci = ev / EPC, rem = ev - ci * EPC, q = rem / NE, e = rem - q * NE, tr = q / 6, kq = q - tr * 6;
+    int ci = tid / EPC, rem = tid - ci * EPC;              // (cell, evaluation in the cell) advanced without a division per round
+    for (int ev = tid; ev < nb * EPC; ev += CQ_THREADS, rem += CQ_THREADS) {
+        while (rem >= EPC) { rem -= EPC; ci++; }
+        const int q = rem / NE, e = rem - q * NE, tr = q / 6, kq = q - tr * 6;
         double *cell = cells + (size_t)ci * L.stride;
         const double *tg = cell + L.tri + tr * 7;
         const double *te = cell + L.trie + (tr * NE + e) * 5;
