@@ -443,15 +443,18 @@ k_amore(DevProblem p, DevTasks t, const int32_t *__restrict__ task_list, int64_t
 // The reference evaluates the strain matrix of element j at every point once for the diagonal block (j,j) and again for every
 // off-diagonal block it takes part in (AMORE.py:59-123): NE evaluations per (point, element).  The values are identical, so here
 // each (point, element) pair is evaluated ONCE.  A CTA takes a batch of CB cells and runs three phases over shared memory:
-//   phase 0  thread per (cell, element): node coordinates -> smem; thread per (cell, triangle, element): triangle corners,
-//            det J, rho_e at the corners and grad(rho_e) (constant on a straight triangle) -> smem.
+//   phase 0  thread per (cell, triangle, element): triangle corners, det J, rho_e at the corners and grad(rho_e) (constant on a
+//            straight triangle) -> smem; the thread of triangle 0 also fetches the element's node coordinates and material id.
+//            Everything is three dependent loads away from the cell record the symbolic phase wrote (CqRec).
 //   phase 1  thread per EVALUATION (cell, point, element): position, rho, Newton inverse map, shape gradients, the compressed
-//            strain pair (gx[4], gy[4]) -> one row of 8 doubles in smem.  Short dependent chains at a register count that
-//            allows 24-32 warps per SM: this is where the fp64 pipe is kept busy.
+//            strain pair (gx[4], gy[4]) -> one record of 8 doubles in smem.  This is where the fp64 pipe is kept busy.
 //   phase 2  four threads per BLOCK (diag j | off (j,l)), each owning one row node = 16 of the block's 64 sums: they walk the
-//            points IN ORDER and accumulate with the same fma sequence as k_amore, reading the rows of elements j and l from
-//            smem, then apply D and store the 2x2 sub-blocks (128 contiguous bytes per thread).  Results are bit-identical to
-//            the thread-per-block kernel.
+//            points IN ORDER and accumulate with the same fma sequence as k_amore, reading the records of elements j and l from
+//            smem, then apply D and store the 2x2 sub-blocks as whole 32-byte records at their positions in the reduction
+//            order (record numbers fetched before the accumulation; a second, transposed record for off-diagonal blocks).
+//            Results are bit-identical to the thread-per-block kernel.
+// A CTA is ONE warp (barriers cost nothing) with a batch of ~4 cells; about 20 CTAs are resident per SM and sit in different
+// phases, so the fp64-dense Newton phase of some overlaps the load latency of phase 0 and the stores of phase 2 of others.
 // Strain-pair records are 10 doubles apart (8 used; 128-bit stores of a quarter warp cover all 32 banks) and the per-cell stride
 // is 4 mod 16 doubles, so the records of neighbouring cells start in different banks.
 // ---------------------------------------------------------------------------------------------------------------
