@@ -305,7 +305,7 @@ int mofem_symbolic(mofem_ctx *ctx)
     CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, 0, s)); L++;   // rank sort of the short rows
     CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKT(cudaStreamSynchronize(s));
-    if (eflag) {                   // some node rows have > 256 contributions: bitonic sort for those
+    if (eflag) {                   // some node rows have > 512 contributions: shared-memory bitonic sort for those
         CKT(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
         CKT(csr_sort_rows(P.n_node, C.row_start, entries, row_uniq, nullptr, ctx->err_flag, 1, s)); L++;
         CKT(cudaMemcpyAsync(&eflag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -9,7 +9,7 @@
 //   2. fill buckets with keys (col_node << 32) | src,  src = (node pair in task order << 1) | transposed
 //      -- src increases in emission order, so sorting the 64-bit key orders a row by (column, emission order)
 //      whatever order the atomics filled the bucket in
-//   3. one warp per row: bitonic sort of the bucket, count distinct columns
+//   3. one warp per row: bitonic sort of the bucket (in registers for rows <= 512, through shared memory above), count distinct columns
 //   4. prefix-sum -> node_ptr; emit node_idx / contrib_ptr / the sorted sources
 //   5. inverse map pair_dst: the record of blk_val every contribution is stored in
 // The integration kernels store every 2x2 block value straight into its record (blk_val is in REDUCTION order: the transposed
@@ -119,34 +119,90 @@ k_sort_rows(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__r
     if (lane == 0) row_uniq[row] = uniq;
 }
 
-// Short rows (<= RANK_MAX contributions; the bench matrix averages 71 per node row): rank sort -- every lane holds up to M of
-// the row's keys in registers and counts, over one broadcast pass through the row in shared memory, how many keys are smaller;
-// the rank IS the sorted position (keys are distinct: src is unique).  No padding to a power of two, no stage barriers:
-// ~2x faster than the bitonic network at these lengths.  Longer rows are left to k_sort_rows (flagged through *long_rows).
+// Rows of <= RANK_MAX contributions (the bench matrix averages 71 per node row, the 3-mesh family 130): bitonic network IN REGISTERS.  A warp sorts
+// one row; lane l holds the M = 2 | 4 | 8 | 16 consecutive keys  l*M .. l*M + M-1  of the row padded to 32*M with ~0.  Compare-exchange
+// steps whose partner is M or more keys away go through shuffles (the partner sits in lane l ^ (stride / M), same slot), closer
+// ones stay inside the lane; no shared-memory traffic and no barriers between the steps -- only the load is staged through
+// shared memory (coalesced read of the row, blocked layout for the lanes).  Measured against the O(L^2) rank sort it replaces
+// (every lane counts, over one broadcast pass through the row, how many keys are smaller than its own): see DESIGN.md.  Longer rows
+// are left to k_sort_rows (flagged through *long_rows).
 constexpr int RANK_WARPS = 8;
-constexpr int RANK_MAX = 256;
+constexpr int RANK_MAX = 512;
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask)
+{
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), lane_mask);
+    return ((uint64_t)hi << 32) | lo;
+}
 
 template <int M>
-__device__ __forceinline__ void warp_rank_sort(const uint64_t *__restrict__ keys, uint64_t *__restrict__ sorted, int L, int lane)
+__device__ __forceinline__ void warp_bitonic_regs(uint64_t (&k)[M], int lane)
+{
+    const int i0 = lane * M;       // index of this lane's first key
+#pragma unroll
+    for (int size = 2; size <= 32 * M; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= M) {     // partner in another lane, same slot
+                const bool up = (i0 & size) == 0, lower = (i0 & stride) == 0;
+                const bool take_min = (up == lower);
+#pragma unroll
+                for (int r = 0; r < M; r++) {
+                    const uint64_t o = shfl_xor_u64(k[r], stride / M);
+                    const bool mine_smaller = k[r] < o;
+                    k[r] = (mine_smaller == take_min) ? k[r] : o;
+                }
+            } else {               // partner inside the lane: slots r and r ^ stride
+#pragma unroll
+                for (int r = 0; r < M; r++) {
+                    if ((r & stride) == 0) {
+                        const int r2 = r | stride;
+                        const bool up = (size >= M) ? ((i0 & size) == 0) : ((r & size) == 0);
+                        const uint64_t a = k[r], c = k[r2];
+                        const bool sw = (a > c) == up;
+                        k[r] = sw ? c : a; k[r2] = sw ? a : c;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// sorts the row staged in `keys` (L valid, padded here), writes it back to entries[b ..] and returns the lane's count of
+// distinct columns
+template <int M>
+__device__ __forceinline__ int sort_row_regs(uint64_t *__restrict__ keys, int L, int lane, uint64_t *__restrict__ out)
 {
     uint64_t k[M];
-    int rank[M];
 #pragma unroll
-    for (int m = 0; m < M; m++) { const int i = lane + 32 * m; k[m] = i < L ? keys[i] : ~0ull; rank[m] = 0; }
-    for (int j = 0; j < L; j++) {
-        const uint64_t kj = keys[j];
-#pragma unroll
-        for (int m = 0; m < M; m++) rank[m] += (kj < k[m]) ? 1 : 0;
+    for (int r = 0; r < M; r++) { const int i = lane * M + r; k[r] = i < L ? keys[i] : ~0ull; }
+    warp_bitonic_regs<M>(k, lane);
+    // the key before this lane's first one (distinct-column test across the lane boundary)
+    uint64_t prev;
+    {
+        const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)k[M - 1], 1);
+        const uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(k[M - 1] >> 32), 1);
+        prev = ((uint64_t)hi << 32) | lo;
     }
+    int uniq = 0;
 #pragma unroll
-    for (int m = 0; m < M; m++) if (lane + 32 * m < L) sorted[rank[m]] = k[m];
+    for (int r = 0; r < M; r++) {
+        const int i = lane * M + r;
+        if (i < L) {
+            out[i] = k[r];
+            if (i == 0 || (uint32_t)(prev >> 32) != (uint32_t)(k[r] >> 32)) uniq++;
+        }
+        prev = k[r];
+    }
+    return uniq;
 }
 
 __global__ void __launch_bounds__(RANK_WARPS * 32)
 k_sort_rows_rank(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t *__restrict__ entries,
                  int32_t *__restrict__ row_uniq, int *long_rows)
 {
-    __shared__ uint64_t sm_in[RANK_WARPS][RANK_MAX], sm_out[RANK_WARPS][RANK_MAX];
+    __shared__ uint64_t sm_in[RANK_WARPS][RANK_MAX];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * RANK_WARPS + w;
     if (row >= n_node) return;
@@ -155,26 +211,14 @@ k_sort_rows_rank(int64_t n_node, const int64_t *__restrict__ row_start, uint64_t
     if (L64 == 0) { if (lane == 0) row_uniq[row] = 0; return; }
     if (L64 > RANK_MAX) { if (lane == 0) *long_rows = 1; return; }
     const int L = (int)L64;
-    uint64_t *keys = sm_in[w], *sorted = sm_out[w];
+    uint64_t *keys = sm_in[w];
     for (int i = lane; i < L; i += 32) keys[i] = entries[b + i];
     __syncwarp();
-    switch ((L + 31) >> 5) {
-    case 1: warp_rank_sort<1>(keys, sorted, L, lane); break;
-    case 2: warp_rank_sort<2>(keys, sorted, L, lane); break;
-    case 3: warp_rank_sort<3>(keys, sorted, L, lane); break;
-    case 4: warp_rank_sort<4>(keys, sorted, L, lane); break;
-    case 5: warp_rank_sort<5>(keys, sorted, L, lane); break;
-    case 6: warp_rank_sort<6>(keys, sorted, L, lane); break;
-    case 7: warp_rank_sort<7>(keys, sorted, L, lane); break;
-    default: warp_rank_sort<8>(keys, sorted, L, lane); break;
-    }
-    __syncwarp();
-    int uniq = 0;
-    for (int i = lane; i < L; i += 32) {
-        const uint64_t kx = sorted[i];
-        entries[b + i] = kx;
-        if (i == 0 || (uint32_t)(sorted[i - 1] >> 32) != (uint32_t)(kx >> 32)) uniq++;
-    }
+    int uniq;
+    if (L <= 64) uniq = sort_row_regs<2>(keys, L, lane, entries + b);
+    else if (L <= 128) uniq = sort_row_regs<4>(keys, L, lane, entries + b);
+    else if (L <= 256) uniq = sort_row_regs<8>(keys, L, lane, entries + b);
+    else uniq = sort_row_regs<16>(keys, L, lane, entries + b);
 #pragma unroll
     for (int d = 16; d; d >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, d);
     if (lane == 0) row_uniq[row] = uniq;
