@@ -38,3 +38,16 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "0", "--n0", "16"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and out.stdout.strip() == ""
+
+
+def test_scaling_decomposition_only_for_the_default_weak_series():
+    """The extra object of the multi-GPU lines exists only where its committed 1-GPU side applies (default weak workload)."""
+    import argparse
+    import bench
+    a = argparse.Namespace(strong=False, family="quad", n0=664)
+    assert bench.scaling_decomposition(a, 1, 6558, 10000.0) is None
+    d = bench.scaling_decomposition(a, 8, 13036, 9043.0)
+    assert d is not None and abs(d["iteration_growth"] - 13036 / d["pcg_iterations_1gpu"]) < 1e-12
+    assert 0.0 < d["per_iteration_efficiency"] < 1.2
+    assert bench.scaling_decomposition(argparse.Namespace(strong=True, family="quad", n0=664), 8, 1, 1.0) is None
+    assert bench.scaling_decomposition(argparse.Namespace(strong=False, family="m3s", n0=664), 8, 1, 1.0) is None
